@@ -1,0 +1,147 @@
+/* swcgpu.h — C ABI of libswcgpu.so: B200 (sm_100a) batched decompression engine that replaces the decode hot path of
+ * tsolomko/SWCompression 4.9.0 (pure Swift).  The reference has no FFI layer; its "operator API" is the set of Swift
+ * static functions cited next to each entry point below.  A Swift / ctypes shim keeps those names and signatures and
+ * routes the bodies through this header (see INTEGRATION.md for the module map + Swift binding).
+ *
+ * Conventions
+ *   - extern "C", no exceptions, no torch types.  Return value / status[] entries are `enum swc_status` codes
+ *     (include/swc_status.h): 0 = OK, <base>+k = k-th case of the corresponding Swift error enum.
+ *   - "payload-carrying" errors (wrongCRC(Data), checksumMismatch([Data]), wrongAdler32(Data), wrongCheck([Data]))
+ *     return the status AND the decoded bytes, as the Swift errors do.
+ *   - single-unit calls take HOST pointers, run on the current device and return a buffer allocated with swc_alloc
+ *     (caller frees with swc_free).  *_batch calls take DEVICE pointers and are asynchronous on `cuda_stream`.
+ *     *_batch_host calls take HOST pointers and include the host<->device copies (blocking).
+ *   - every decode reports how much input it consumed, because the reference's wrappers keep parsing after the
+ *     payload (GzipArchive.swift:88-94, ZlibArchive.swift:31-37, ZipContainer.swift:74-79, XZBlock.swift:78-82).
+ *   - there is no CPU fallback: without a CUDA device every call returns SWC_ERR_NO_DEVICE.
+ *
+ * Batch layout (all arrays have n entries, device memory):
+ *   unit i reads  in_base[in_off[i] .. in_off[i]+in_len[i])           (any byte alignment; 16-B aligned is fastest)
+ *   unit i writes out_base[out_off[i] .. out_off[i]+out_cap[i])       (out_off[i] must be a multiple of 16)
+ *   results: out_len[i] (bytes produced; on SWC_ERR_OUTPUT_OVERFLOW the size required), consumed[i], status[i].
+ *   Output regions must not overlap.  Bytes between out_len[i] and out_cap[i] are scratch and may be clobbered.
+ */
+#ifndef SWCGPU_H
+#define SWCGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "swc_status.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library / memory ---- */
+int32_t     swc_device_count(void);
+int32_t     swc_set_device(int32_t device);
+const char *swc_last_error_string(void);               /* thread-local text for the last SWC_ERR_CUDA */
+const char *swc_status_name(int32_t status);           /* "DeflateError.wrongSymbol", ... */
+void       *swc_alloc(size_t bytes);                   /* host memory for single-unit results */
+void        swc_free(void *p);
+void       *swc_alloc_pinned(size_t bytes);            /* page-locked host memory for *_batch_host callers */
+void        swc_free_pinned(void *p);
+uint64_t    swc_kernel_launches(void);                 /* number of CUDA kernels this library has launched so far */
+int32_t     swc_release_scratch(void);                 /* free the per-device scratch pools */
+
+/* ---- Deflate ------------------------------------------------------------------------------------------------
+ * Deflate.decompress(data:)                Sources/Deflate/Deflate.swift:24-28
+ * Deflate.decompress(_: LsbBitReader)      Sources/Deflate/Deflate.swift:30-249   (start_bit/consumed_bits form) */
+int32_t swc_deflate_decompress(const uint8_t *in, size_t in_len, size_t start_bit,
+                               uint8_t **out, size_t *out_len, size_t *consumed_bits);
+/* scratch the batched call needs for `out_capacity_total` bytes of output buffer */
+size_t  swc_deflate_batch_scratch_bytes(uint64_t n, uint64_t out_capacity_total);
+int32_t swc_deflate_decompress_batch(const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len,
+                                     const uint8_t *start_bits /* n entries 0..7, or NULL */,
+                                     uint8_t *out_base, const uint64_t *out_off, const uint64_t *out_cap,
+                                     uint64_t out_capacity_total,
+                                     uint64_t *out_len, uint64_t *consumed_bits, int32_t *status,
+                                     uint64_t n, void *scratch, size_t scratch_bytes /* NULL,0 = library pool */,
+                                     void *cuda_stream);
+int32_t swc_deflate_decompress_batch_host(const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len,
+                                          uint64_t in_total,
+                                          uint8_t *out_base, const uint64_t *out_off, const uint64_t *out_cap,
+                                          uint64_t out_capacity_total,
+                                          uint64_t *out_len, uint64_t *consumed_bits, int32_t *status, uint64_t n);
+
+/* ---- LZ4 ----------------------------------------------------------------------------------------------------
+ * LZ4.decompress(data:)                                   Sources/LZ4/LZ4.swift:49-51
+ * LZ4.decompress(data:dictionary:dictionaryID:)           Sources/LZ4/LZ4.swift:73-91
+ * LZ4.multiDecompress(data:dictionary:dictionaryID:)      Sources/LZ4/LZ4.swift:116-146
+ * LZ4.process(block:_:) (private raw-block decoder)       Sources/LZ4/LZ4.swift:332-413  -> *_block_batch */
+int32_t swc_lz4_decompress(const uint8_t *in, size_t in_len, const uint8_t *dict /* NULL = nil */, size_t dict_len,
+                           int32_t has_dict_id, uint32_t dict_id,
+                           uint8_t **out, size_t *out_len, size_t *consumed_bytes);
+/* frames are concatenated into *out; frame_ends[i] = end offset of frame i; returns the number of frames in *n_frames */
+int32_t swc_lz4_multi_decompress(const uint8_t *in, size_t in_len, const uint8_t *dict, size_t dict_len,
+                                 int32_t has_dict_id, uint32_t dict_id,
+                                 uint8_t **out, size_t *out_len, size_t **frame_ends, size_t *n_frames);
+/* raw blocks; dict (device pointer, may be NULL) is the prefix every block may reference (independent-block mode) */
+int32_t swc_lz4_block_decompress_batch(const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len,
+                                       const uint8_t *dict, uint64_t dict_len,
+                                       uint8_t *out_base, const uint64_t *out_off, const uint64_t *out_cap,
+                                       uint64_t *out_len, int32_t *status, uint64_t n, void *cuda_stream);
+int32_t swc_lz4_block_decompress_batch_host(const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len,
+                                            uint64_t in_total,
+                                            uint8_t *out_base, const uint64_t *out_off, const uint64_t *out_cap,
+                                            uint64_t out_capacity_total,
+                                            uint64_t *out_len, int32_t *status, uint64_t n);
+
+/* ---- BZip2 --------------------------------------------------------------------------------------------------
+ * BZip2.decompress(data:)            Sources/BZip2/BZip2.swift:22-26
+ * BZip2.multiDecompress(data:)       Sources/BZip2/BZip2.swift:40-48
+ * BZip2.decompress(_: MsbBitReader)  Sources/BZip2/BZip2.swift:50-95 */
+int32_t swc_bzip2_decompress(const uint8_t *in, size_t in_len, size_t start_bit,
+                             uint8_t **out, size_t *out_len, size_t *consumed_bits);
+int32_t swc_bzip2_multi_decompress(const uint8_t *in, size_t in_len,
+                                   uint8_t **out, size_t *out_len, size_t **stream_ends, size_t *n_streams);
+/* one .bz2 stream per unit */
+int32_t swc_bzip2_decompress_batch(const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len,
+                                   uint8_t *out_base, const uint64_t *out_off, const uint64_t *out_cap,
+                                   uint64_t *out_len, uint64_t *consumed_bits, int32_t *status,
+                                   uint64_t n, void *cuda_stream);
+
+/* ---- LZMA / LZMA2 -------------------------------------------------------------------------------------------
+ * LZMA.decompress(data:)                                   Sources/LZMA/LZMA.swift:25-34
+ * LZMA.decompress(data:properties:uncompressedSize:)       Sources/LZMA/LZMA.swift:56-61
+ * LZMA2.decompress(data:)                                  Sources/LZMA2/LZMA2.swift:25-30
+ * LZMA2.decompress(_:_:) (reader + dict byte, used by XZ)  Sources/LZMA2/LZMA2.swift:32-36 */
+int32_t swc_lzma_decompress(const uint8_t *in, size_t in_len, uint8_t **out, size_t *out_len, size_t *consumed_bytes);
+int32_t swc_lzma_decompress_raw(const uint8_t *in, size_t in_len, int32_t lc, int32_t lp, int32_t pb,
+                                int64_t dictionary_size, int64_t uncompressed_size /* <0 = nil */,
+                                uint8_t **out, size_t *out_len, size_t *consumed_bytes);
+int32_t swc_lzma2_decompress(const uint8_t *in, size_t in_len, uint8_t **out, size_t *out_len, size_t *consumed_bytes);
+/* one raw LZMA2 stream per unit; dict_bytes[i] is the XZ filter property byte */
+int32_t swc_lzma2_decompress_batch(const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len,
+                                   const uint8_t *dict_bytes,
+                                   uint8_t *out_base, const uint64_t *out_off, const uint64_t *out_cap,
+                                   uint64_t *out_len, uint64_t *consumed_bytes, int32_t *status,
+                                   uint64_t n, void *cuda_stream);
+
+/* ---- wrappers -----------------------------------------------------------------------------------------------
+ * GzipArchive.unarchive(archive:) / multiUnarchive   Sources/GZip/GzipArchive.swift:38-77
+ * ZlibArchive.unarchive(archive:)                     Sources/Zlib/ZlibArchive.swift:25-42
+ * XZArchive.unarchive(archive:) / splitUnarchive      Sources/XZ/XZArchive.swift:27-88 */
+int32_t swc_gzip_unarchive(const uint8_t *in, size_t in_len, uint8_t **out, size_t *out_len, size_t *consumed_bytes);
+int32_t swc_gzip_multi_unarchive(const uint8_t *in, size_t in_len,
+                                 uint8_t **out, size_t *out_len, size_t **member_ends, size_t *n_members);
+int32_t swc_zlib_unarchive(const uint8_t *in, size_t in_len, uint8_t **out, size_t *out_len);
+int32_t swc_xz_unarchive(const uint8_t *in, size_t in_len, uint8_t **out, size_t *out_len);
+int32_t swc_xz_split_unarchive(const uint8_t *in, size_t in_len,
+                               uint8_t **out, size_t *out_len, size_t **stream_ends, size_t *n_streams);
+
+/* ---- checks (device-side, used by the wrappers; exposed for the shim and the tests) ---------------------------
+ * CheckSums.crc32 / bzip2crc32 / crc64 / adler32   Sources/Common/CheckSums.swift:12-57
+ * XxHash32.hash                                     Sources/LZ4/XxHash32.swift:24-83
+ * Sha256.hash                                       Sources/XZ/Sha256.swift */
+int32_t swc_crc32(const uint8_t *in, size_t n, uint32_t *result);
+int32_t swc_bzip2_crc32(const uint8_t *in, size_t n, uint32_t *result);
+int32_t swc_crc64(const uint8_t *in, size_t n, uint64_t *result);
+int32_t swc_adler32(const uint8_t *in, size_t n, uint32_t *result);
+int32_t swc_xxh32(const uint8_t *in, size_t n, uint32_t *result);
+int32_t swc_sha256(const uint8_t *in, size_t n, uint8_t digest[32]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWCGPU_H */

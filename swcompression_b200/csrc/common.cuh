@@ -1,0 +1,46 @@
+// common.cuh — shared device/host helpers for libswcgpu (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/swc_status.h"
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int64_t i64;
+
+#define SWC_WARP 32
+#define SWC_FULL 0xFFFFFFFFu
+
+// internal status: unit needs the generic (slow) decoder — never escapes the library
+#define SWC_INTERNAL_NEEDS_SLOW 9001
+
+namespace swc {
+
+__device__ __forceinline__ uint4 ldg16(const uint4 *p) { return __ldg(p); }
+
+// streaming 16-byte load that does not pollute L1 (compressed input is read exactly once)
+__device__ __forceinline__ uint4 ld_stream16(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
+
+// launch bookkeeping (swc_kernel_launches)
+void count_launch(int n = 1);
+// record a CUDA failure; returns SWC_ERR_CUDA
+int cuda_fail(cudaError_t e, const char *where);
+
+#define SWC_CUDA_TRY(expr)                                                     \
+    do {                                                                       \
+        cudaError_t _e = (expr);                                               \
+        if (_e != cudaSuccess) return swc::cuda_fail(_e, #expr);               \
+    } while (0)
+
+// scratch pool: grow-only per-device buffer, used when the caller passes no scratch
+int scratch_get(size_t bytes, void **p, cudaStream_t stream);
+
+}  // namespace swc

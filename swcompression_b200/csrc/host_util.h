@@ -1,0 +1,48 @@
+// host_util.h — host-side helpers shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <vector>
+#include "common.cuh"
+
+namespace swc {
+
+int ensure_device();
+
+// RAII device allocation (single-unit paths; the batch paths use caller memory + the scratch pool)
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    int alloc(size_t n) {
+        release();
+        cudaError_t e = cudaMalloc(&p, n ? n : 16);
+        if (e != cudaSuccess) { p = nullptr; return cuda_fail(e, "cudaMalloc"); }
+        bytes = n;
+        return SWC_OK;
+    }
+    template <typename T> T *as() const { return (T *)p; }
+};
+
+// result of decoding ONE unit that is already resident on the device
+struct UnitResult {
+    DevBuf out;            // decoded bytes (device)
+    size_t out_len = 0;
+    size_t consumed = 0;   // bits (Deflate/BZip2) or bytes (LZ4/LZMA)
+    int status = 0;
+};
+
+// Deflate stream starting at byte `start` + `start_bit` bits inside d_in[0..in_len)
+int deflate_unit_device(const u8 *d_in, size_t in_len, size_t start_bit_abs, UnitResult &r, size_t hint = 0);
+
+inline size_t round16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+// hand a device buffer back to a C caller as swc_alloc'ed host memory
+int to_host_alloc(const void *d, size_t n, uint8_t **out, size_t *out_len);
+
+}  // namespace swc

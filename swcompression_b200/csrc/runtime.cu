@@ -1,0 +1,157 @@
+// runtime.cu — library plumbing: error text, launch counter, host/pinned allocators, scratch pool, status names.
+#include <mutex>
+#include <string>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include "common.cuh"
+#include "../../include/swcgpu.h"
+#include "host_util.h"
+
+namespace swc {
+
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int cuda_fail(cudaError_t e, const char *where) {
+    g_err = std::string(where) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();   // clear sticky-less errors
+    return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? SWC_ERR_NO_DEVICE : SWC_ERR_CUDA;
+}
+
+// ---- grow-only scratch pool, one per device ----
+struct Pool { void *p = nullptr; size_t bytes = 0; };
+static std::mutex g_pool_mu;
+static Pool g_pools[64];
+
+int scratch_get(size_t bytes, void **p, cudaStream_t stream) {
+    int dev = 0;
+    SWC_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    Pool &pool = g_pools[dev & 63];
+    if (pool.bytes < bytes) {
+        if (pool.p) {
+            SWC_CUDA_TRY(cudaStreamSynchronize(stream));
+            SWC_CUDA_TRY(cudaDeviceSynchronize());
+            cudaFree(pool.p);
+            pool.p = nullptr; pool.bytes = 0;
+        }
+        size_t want = bytes + (bytes >> 3) + (1 << 20);
+        cudaError_t e = cudaMalloc(&pool.p, want);
+        if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&pool.p, want); }
+        if (e != cudaSuccess) { pool.p = nullptr; return cuda_fail(e, "cudaMalloc(scratch)"); }
+        pool.bytes = want;
+    }
+    *p = pool.p;
+    return SWC_OK;
+}
+
+int ensure_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_err = "no CUDA device (libswcgpu has no CPU fallback)";
+        cudaGetLastError();
+        return SWC_ERR_NO_DEVICE;
+    }
+    return SWC_OK;
+}
+
+}  // namespace swc
+
+extern "C" {
+
+int32_t swc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int32_t swc_set_device(int32_t device) {
+    if (swc::ensure_device()) return SWC_ERR_NO_DEVICE;
+    SWC_CUDA_TRY(cudaSetDevice(device));
+    return SWC_OK;
+}
+const char *swc_last_error_string(void) { return swc::g_err.c_str(); }
+void *swc_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
+void swc_free(void *p) { free(p); }
+void *swc_alloc_pinned(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void swc_free_pinned(void *p) { if (p) cudaFreeHost(p); }
+uint64_t swc_kernel_launches(void) { return swc::g_launches.load(); }
+int32_t swc_release_scratch(void) {
+    std::lock_guard<std::mutex> lk(swc::g_pool_mu);
+    for (auto &pool : swc::g_pools) {
+        if (pool.p) { cudaFree(pool.p); pool.p = nullptr; pool.bytes = 0; }
+    }
+    return SWC_OK;
+}
+
+const char *swc_status_name(int32_t s) {
+    switch (s) {
+    case SWC_OK: return "ok";
+    case SWC_ERR_OUTPUT_OVERFLOW: return "engine.outputOverflow";
+    case SWC_ERR_REFERENCE_TRAP: return "engine.referenceTrap";
+    case SWC_ERR_CUDA: return "engine.cuda";
+    case SWC_ERR_INVALID_ARG: return "engine.invalidArgument";
+    case SWC_ERR_NO_DEVICE: return "engine.noDevice";
+    case SWC_ERR_UNSUPPORTED: return "engine.unsupported";
+    case SWC_DEFLATE_WRONG_UNCOMPRESSED_BLOCK_LENGTHS: return "DeflateError.wrongUncompressedBlockLengths";
+    case SWC_DEFLATE_WRONG_BLOCK_TYPE: return "DeflateError.wrongBlockType";
+    case SWC_DEFLATE_WRONG_SYMBOL: return "DeflateError.wrongSymbol";
+    case SWC_DEFLATE_SYMBOL_NOT_FOUND: return "DeflateError.symbolNotFound";
+    case SWC_BZIP2_WRONG_MAGIC: return "BZip2Error.wrongMagic";
+    case SWC_BZIP2_WRONG_VERSION: return "BZip2Error.wrongVersion";
+    case SWC_BZIP2_WRONG_BLOCK_SIZE: return "BZip2Error.wrongBlockSize";
+    case SWC_BZIP2_WRONG_BLOCK_TYPE: return "BZip2Error.wrongBlockType";
+    case SWC_BZIP2_RANDOMIZED_BLOCK: return "BZip2Error.randomizedBlock";
+    case SWC_BZIP2_WRONG_HUFFMAN_GROUPS: return "BZip2Error.wrongHuffmanGroups";
+    case SWC_BZIP2_WRONG_SELECTOR: return "BZip2Error.wrongSelector";
+    case SWC_BZIP2_WRONG_HUFFMAN_CODE_LENGTH: return "BZip2Error.wrongHuffmanCodeLength";
+    case SWC_BZIP2_SYMBOL_NOT_FOUND: return "BZip2Error.symbolNotFound";
+    case SWC_BZIP2_WRONG_CRC: return "BZip2Error.wrongCRC";
+    case SWC_LZMA_WRONG_PROPERTIES: return "LZMAError.wrongProperties";
+    case SWC_LZMA_RANGE_DECODER_INIT_ERROR: return "LZMAError.rangeDecoderInitError";
+    case SWC_LZMA_EXCEEDED_UNCOMPRESSED_SIZE: return "LZMAError.exceededUncompressedSize";
+    case SWC_LZMA_WINDOW_IS_EMPTY: return "LZMAError.windowIsEmpty";
+    case SWC_LZMA_RANGE_DECODER_FINISH_ERROR: return "LZMAError.rangeDecoderFinishError";
+    case SWC_LZMA_REPEAT_WILL_EXCEED: return "LZMAError.repeatWillExceed";
+    case SWC_LZMA_NOT_ENOUGH_TO_REPEAT: return "LZMAError.notEnoughToRepeat";
+    case SWC_LZMA2_WRONG_DICTIONARY_SIZE: return "LZMA2Error.wrongDictionarySize";
+    case SWC_LZMA2_WRONG_CONTROL_BYTE: return "LZMA2Error.wrongControlByte";
+    case SWC_LZMA2_WRONG_RESET: return "LZMA2Error.wrongReset";
+    case SWC_LZMA2_WRONG_SIZES: return "LZMA2Error.wrongSizes";
+    case SWC_DATA_TRUNCATED: return "DataError.truncated";
+    case SWC_DATA_CORRUPTED: return "DataError.corrupted";
+    case SWC_DATA_CHECKSUM_MISMATCH: return "DataError.checksumMismatch";
+    case SWC_DATA_UNSUPPORTED_FEATURE: return "DataError.unsupportedFeature";
+    case SWC_GZIP_WRONG_MAGIC: return "GzipError.wrongMagic";
+    case SWC_GZIP_WRONG_COMPRESSION_METHOD: return "GzipError.wrongCompressionMethod";
+    case SWC_GZIP_WRONG_FLAGS: return "GzipError.wrongFlags";
+    case SWC_GZIP_WRONG_HEADER_CRC: return "GzipError.wrongHeaderCRC";
+    case SWC_GZIP_WRONG_CRC: return "GzipError.wrongCRC";
+    case SWC_GZIP_WRONG_ISIZE: return "GzipError.wrongISize";
+    case SWC_GZIP_CANNOT_ENCODE_ISO_LATIN1: return "GzipError.cannotEncodeISOLatin1";
+    case SWC_ZLIB_WRONG_COMPRESSION_METHOD: return "ZlibError.wrongCompressionMethod";
+    case SWC_ZLIB_WRONG_COMPRESSION_INFO: return "ZlibError.wrongCompressionInfo";
+    case SWC_ZLIB_WRONG_FCHECK: return "ZlibError.wrongFcheck";
+    case SWC_ZLIB_WRONG_COMPRESSION_LEVEL: return "ZlibError.wrongCompressionLevel";
+    case SWC_ZLIB_WRONG_ADLER32: return "ZlibError.wrongAdler32";
+    case SWC_XZ_WRONG_MAGIC: return "XZError.wrongMagic";
+    case SWC_XZ_WRONG_FIELD: return "XZError.wrongField";
+    case SWC_XZ_WRONG_INFO_CRC: return "XZError.wrongInfoCRC";
+    case SWC_XZ_WRONG_FILTER_ID: return "XZError.wrongFilterID";
+    case SWC_XZ_CHECK_TYPE_SHA256: return "XZError.checkTypeSHA256";
+    case SWC_XZ_WRONG_DATA_SIZE: return "XZError.wrongDataSize";
+    case SWC_XZ_WRONG_CHECK: return "XZError.wrongCheck";
+    case SWC_XZ_WRONG_PADDING: return "XZError.wrongPadding";
+    case SWC_XZ_MULTI_BYTE_INTEGER_ERROR: return "XZError.multiByteIntegerError";
+    default: return "unknown";
+    }
+}
+
+}  // extern "C"

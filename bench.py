@@ -1,0 +1,354 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the hot path (BASELINE.json config 2): batched Deflate decode of independent
+64 KiB dynamic-Huffman blocks on B200, measured as decompressed GB/s (10^9 B/s).
+
+    python bench.py --gpus N --steps K --warmup W            # product arm (CUDA, through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...   # reference arm: the reference's algorithm on host cores
+
+One "step" = one batched call of the hot path over the whole workload (262 144 units x 65 536 B = 16 GiB decoded per
+GPU; 4096 distinct synthetic units tiled x64 on the device to bound host prep time).  `value` is measured with the
+compressed batch resident in HBM; `e2e` goes through swc_deflate_decompress_batch_host with pinned HOST buffers, i.e.
+host->device and device->host copies inside the timed region (on a 1/4-size batch, stated in config).
+Multi-GPU: units are independent, every rank decodes its own shard with no data-path collective (weak scaling);
+NCCL is used for the barrier and the max-over-ranks time only.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import time
+from concurrent.futures import ThreadPoolExecutor
+from multiprocessing import Pool
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+UNIT = 65536
+N_UNITS = 262144          # BASELINE.json configs[1]
+DISTINCT = 4096
+METRIC = "decompressed_GB_per_s"
+
+
+def _make_unit(seed):
+    import helpers as H
+    raw = H.textlike(UNIT, seed)
+    comp = H.raw_deflate(raw)           # zlib level 6, raw deflate, memLevel 9 -> one final dynamic block
+    assert comp[0] & 7 == 0b101
+    return comp
+
+
+def make_corpus(distinct, seed0=2):
+    procs = min(os.cpu_count() or 1, 32)
+    with Pool(procs) as pool:
+        return pool.map(_make_unit, range(seed0, seed0 + distinct), chunksize=16)
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------- CPU legs (oracle)
+def cpu_decode_throughput(units, seconds_budget, threads):
+    """Times the CPU restatement of the reference (oracle/) on `threads` host threads over a bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import swco
+    swco.lib()
+
+    def work(u):
+        st, out, _ = swco.deflate_decompress(u)
+        assert st == 0
+        return len(out)
+
+    t0 = time.perf_counter()
+    done_bytes = 0
+    nunits = 0
+    with ThreadPoolExecutor(threads) as ex:
+        chunk = max(threads * 4, 64)
+        i = 0
+        while True:
+            batch = [units[(i + k) % len(units)] for k in range(chunk)]
+            i += chunk
+            done_bytes += sum(ex.map(work, batch))
+            nunits += chunk
+            if time.perf_counter() - t0 >= seconds_budget:
+                break
+    dt = time.perf_counter() - t0
+    return done_bytes / dt / 1e9, nunits, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    units = make_corpus(256)
+    cores = os.cpu_count() or 1
+    per_step = 6.0
+    cpu_decode_throughput(units, 1.0, cores)   # warm
+    vals, n_total = [], 0
+    for _ in range(args.steps):
+        v, n, dt = cpu_decode_throughput(units, per_step, cores)
+        vals.append(v); n_total += n
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "batched Deflate: independent 64 KiB dynamic-Huffman blocks (BASELINE configs[1] shape)",
+                   "note": "the Swift reference cannot be built here (no Swift toolchain); this arm times the C restatement of its "
+                           "algorithm (oracle/, bit-by-bit tree walk like DecodingTree.findNextSymbol) on all host threads"},
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_total} units of 64 KiB in {args.steps} steps of ~{per_step:.0f} s"},
+        "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------- product arm
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+    from swcompression_b200 import _lib
+    from swcompression_b200.batch import Batch, pack_units
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    n_units = args.units
+    distinct = min(args.distinct, n_units)
+    tile = n_units // distinct
+    n_units = tile * distinct
+    units = make_corpus(distinct, seed0=2 + 100000 * rank)      # fork the generator pool BEFORE CUDA is initialised
+    assert torch.cuda.is_available(), "bench.py product arm needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    L.swc_timing_collect.argtypes = [C.c_void_p, C.c_int32]
+
+    buf, offs, lens = pack_units(units)
+    in_bytes_distinct = int(lens.sum())
+    stride = len(buf) - 64
+    # tile the compressed corpus on the device: unit j of tile t lives at offs[j] + t * stride
+    d_one = torch.from_numpy(buf[:stride]).to(dev)
+    d_in = d_one.repeat(tile)
+    d_in = torch.cat([d_in, torch.zeros(64, dtype=torch.uint8, device=dev)])
+    all_off = (offs[None, :] + (np.arange(tile, dtype=np.uint64) * np.uint64(stride))[:, None]).reshape(-1)
+    all_len = np.tile(lens, tile)
+    b = Batch.__new__(Batch)
+    Batch.__init__(b, "deflate", np.zeros(1, dtype=np.uint8), all_off, all_len, UNIT, device=str(dev))
+    b.d_in = d_in
+    total_in = in_bytes_distinct * tile
+    total_out = n_units * UNIT
+    torch.cuda.synchronize(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        b.run()
+    barrier()
+    # parity spot-check of the workload itself against the oracle (outside the timed region)
+    st, ln, used = b.results()
+    assert (st == 0).all() and (ln == UNIT).all(), "decode failed"
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import swco
+    host_out = b.d_out[: 64 * UNIT].cpu().numpy()
+    for i in range(0, 64, 7):
+        ost, oout, oused = swco.deflate_decompress(units[i])
+        assert ost == 0 and bytes(host_out[i * UNIT:(i + 1) * UNIT]) == oout and used[i] == oused, "parity vs oracle failed"
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = L.swc_kernel_launches()
+    L.swc_timing_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        b.run()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    tbuf = (C.c_float * (args.steps * 5 + 8))()
+    nint = L.swc_timing_collect(tbuf, len(tbuf))
+    L.swc_timing_enable(0)
+    launches = L.swc_kernel_launches() - launches0
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    ms_per_step = ms_max / args.steps
+    value = total_out * world / (ms_per_step * 1e-3) / 1e9
+
+    # per-kernel durations: 4 marks per step -> intervals [K1 huffman, slow-path no-op, K2 lz resolve, gap to next step]
+    iv = np.array(list(tbuf)[:nint], dtype=np.float64)
+    k1 = float(iv[0::4].mean()) if nint >= 3 else None
+    ks = float(iv[1::4].mean()) if nint >= 3 else None
+    k2 = float(iv[2::4].mean()) if nint >= 3 else None
+    peak, peak_src = read_peaks()
+    alg_bytes = total_in + total_out
+    roof = None
+    if k1:
+        dom, dom_ms = ("inflate_huffman_kernel", k1) if k1 >= k2 else ("lz_resolve_kernel", k2)
+        achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+        path = alg_bytes / ((k1 + ks + k2) * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(dom)
+            except Exception:
+                traffic = None
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": dom, "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "kernels_ms": {"inflate_huffman_kernel": k1, "inflate_slow_kernel(no-op)": ks, "lz_resolve_kernel": k2},
+                "path_achieved": path, "path_frac": path / peak,
+                "read_only_frac": total_in / ((k1 + ks + k2) * 1e-3) / 1e9 / peak,
+                "write_only_frac": total_out / ((k1 + ks + k2) * 1e-3) / 1e9 / peak}
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region) ----
+    e2e = None
+    if not args.no_e2e:
+        n_e = min(args.e2e_units, n_units)
+        n_e = (n_e // distinct) * distinct if n_e >= distinct else n_e
+        tile_e = max(n_e // distinct, 1)
+        n_e = min(tile_e * distinct, n_units)
+        in_total = stride * tile_e + 64
+        out_total = n_e * UNIT
+        p_in = L.swc_alloc_pinned(in_total)
+        p_out = L.swc_alloc_pinned(out_total)
+        assert p_in and p_out, "pinned allocation failed"
+        h_in = np.ctypeslib.as_array(C.cast(p_in, C.POINTER(C.c_uint8)), shape=(in_total,))
+        for k in range(tile_e):
+            h_in[k * stride:(k + 1) * stride] = buf[:stride]
+        e_off = np.ascontiguousarray(all_off[:n_e]); e_len = np.ascontiguousarray(all_len[:n_e])
+        o_off = (np.arange(n_e, dtype=np.uint64) * np.uint64(UNIT)); o_cap = np.full(n_e, UNIT, dtype=np.uint64)
+        r_len = np.zeros(n_e, dtype=np.uint64); r_used = np.zeros(n_e, dtype=np.uint64); r_st = np.zeros(n_e, dtype=np.int32)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+
+        def call():
+            rc = L.swc_deflate_decompress_batch_host(C.c_void_p(p_in), vp(e_off), vp(e_len), in_total, C.c_void_p(p_out), vp(o_off), vp(o_cap),
+                                                     out_total, vp(r_len), vp(r_used), vp(r_st), n_e)
+            assert rc == 0, _lib.status_name(rc)
+
+        call()
+        assert (r_st == 0).all() and (r_len == UNIT).all()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            call()
+        torch.cuda.synchronize(dev)
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": out_total * world / float(tt.item()) / 1e9, "unit": "GB/s",
+               "h2d_bytes_per_step": int(in_total + n_e * 8 * 4), "d2h_bytes_per_step": int(out_total + n_e * 20),
+               "units_per_step": int(n_e), "ms_per_step": float(tt.item()) * 1e3,
+               "api": "swc_deflate_decompress_batch_host (pinned host buffers; cudaMalloc + H2D + K1/K2 + D2H per call)"}
+        L.swc_free_pinned(C.c_void_p(p_in)); L.swc_free_pinned(C.c_void_p(p_out))
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        v1, n1, dt1 = cpu_decode_throughput(units[:256], 6.0, 1)
+        vN, nN, dtN = cpu_decode_throughput(units[:256], 10.0, cores)
+        cpu = {"value": vN, "unit": "GB/s", "cores": cores, "kind": "port",
+               "sample": f"{nN} units of 64 KiB (same generator/compressor as the GPU workload) in {dtN:.1f} s on {cores} threads",
+               "single_thread_value": v1,
+               "note": "C restatement of the Swift reference's algorithm (oracle/); the Swift reference itself cannot be built here"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"batched Deflate: {n_units} independent 64 KiB single-block dynamic-Huffman units per GPU "
+                                   f"(BASELINE configs[1]); {distinct} distinct units tiled x{tile} on the device",
+                       "units_per_gpu": n_units, "unit_bytes": UNIT, "compressed_bytes_per_gpu": total_in,
+                       "decompressed_bytes_per_gpu": total_out, "parallelism": f"independent units sharded over {world} GPU(s), no collective",
+                       "l2": "inputs+outputs (>20 GB) exceed the 126 MB L2; no flush needed",
+                       "corpus": "order-1 Markov/Zipf text + back-references (tests/helpers.textlike), zlib level 6 raw deflate memLevel 9"},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--units", type=int, default=N_UNITS)
+    ap.add_argument("--distinct", type=int, default=DISTINCT)
+    ap.add_argument("--e2e-units", type=int, default=65536)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_product(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -43,6 +43,10 @@ void       *swc_alloc_pinned(size_t bytes);            /* page-locked host memor
 void        swc_free_pinned(void *p);
 uint64_t    swc_kernel_launches(void);                 /* number of CUDA kernels this library has launched so far */
 int32_t     swc_release_scratch(void);                 /* free the per-device scratch pools */
+/* measurement aid: while enabled, every batched call drops CUDA events on its stream before/between/after its kernels;
+ * swc_timing_collect (after a stream sync) returns the elapsed ms of each interval in launch order */
+void        swc_timing_enable(int32_t on);
+int32_t     swc_timing_collect(float *ms, int32_t max_n);
 
 /* ---- Deflate ------------------------------------------------------------------------------------------------
  * Deflate.decompress(data:)                Sources/Deflate/Deflate.swift:24-28

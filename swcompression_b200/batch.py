@@ -30,9 +30,9 @@ def pack_units(units, align=16):
 
 
 class Batch:
-    """Device-resident batch for one codec ('deflate', 'lz4_block')."""
+    """Device-resident batch for one codec ('deflate', 'lz4_block', 'bzip2', 'lzma2')."""
 
-    def __init__(self, codec, in_buf, in_off, in_len, out_cap, device="cuda:0"):
+    def __init__(self, codec, in_buf, in_off, in_len, out_cap, device="cuda:0", aux=None):
         self.codec = codec
         self.device = torch.device(device)
         self.n = len(in_off)
@@ -54,14 +54,15 @@ class Batch:
         self.d_consumed = torch.zeros(self.n, dtype=torch.int64, device=self.device)
         self.d_status = torch.full((self.n,), -1, dtype=torch.int32, device=self.device)
         self.d_scratch = None
+        self.d_aux = None if aux is None else torch.from_numpy(np.asarray(aux, dtype=np.uint8)).to(self.device)
         if codec == "deflate":
             nbytes = _lib.lib().swc_deflate_batch_scratch_bytes(self.n, self.out_total)
             self.d_scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
 
     @classmethod
-    def from_units(cls, codec, units, out_cap, device="cuda:0"):
+    def from_units(cls, codec, units, out_cap, device="cuda:0", aux=None):
         buf, offs, lens = pack_units(units)
-        return cls(codec, buf, offs, lens, out_cap, device)
+        return cls(codec, buf, offs, lens, out_cap, device, aux)
 
     def run(self):
         L = _lib.lib()
@@ -76,6 +77,12 @@ class Batch:
             st = L.swc_lz4_block_decompress_batch(p(self.d_in), p(self.d_in_off), p(self.d_in_len), None, 0, p(self.d_out),
                                                   p(self.d_out_off), p(self.d_out_cap), p(self.d_out_len), p(self.d_status),
                                                   self.n, stream)
+        elif self.codec == "bzip2":
+            st = L.swc_bzip2_decompress_batch(p(self.d_in), p(self.d_in_off), p(self.d_in_len), p(self.d_out), p(self.d_out_off),
+                                              p(self.d_out_cap), p(self.d_out_len), p(self.d_consumed), p(self.d_status), self.n, stream)
+        elif self.codec == "lzma2":
+            st = L.swc_lzma2_decompress_batch(p(self.d_in), p(self.d_in_off), p(self.d_in_len), p(self.d_aux), p(self.d_out), p(self.d_out_off),
+                                              p(self.d_out_cap), p(self.d_out_len), p(self.d_consumed), p(self.d_status), self.n, stream)
         else:
             raise ValueError(self.codec)
         if st != 0:

@@ -1,0 +1,136 @@
+// api_bzip2.cu — C ABI for BZip2 (include/swcgpu.h): batched device call, single stream, multi-stream.
+#include <cstring>
+#include <vector>
+#include "../../include/swcgpu.h"
+#include "host_util.h"
+#include "bzip2.cuh"
+
+using namespace swc;
+
+namespace {
+
+int bzip2_batch_impl(const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len,
+                     uint8_t *out_base, const uint64_t *out_off, const uint64_t *out_cap,
+                     uint64_t *out_len, uint64_t *consumed_bits, int32_t *status, uint64_t n, cudaStream_t stream) {
+    if (n == 0) return SWC_OK;
+    if (!in_base || !in_off || !in_len || !out_base || !out_off || !out_cap || !out_len || !consumed_bits || !status)
+        return SWC_ERR_INVALID_ARG;
+    // per-unit scratch sizes depend on the capacities: fetch them (n x 8 bytes), lay the scratch out on the host
+    std::vector<uint64_t> caps(n), soff(n);
+    SWC_CUDA_TRY(cudaMemcpyAsync(caps.data(), out_cap, n * 8, cudaMemcpyDeviceToHost, stream));
+    SWC_CUDA_TRY(cudaStreamSynchronize(stream));
+    size_t total = (n * 8 + 255) & ~(size_t)255;
+    for (uint64_t i = 0; i < n; i++) { soff[i] = total; total += bzip2::scratch_per_unit(caps[i]); }
+    void *scratch = nullptr;
+    int st = scratch_get(total, &scratch, stream);
+    if (st) return st;
+    SWC_CUDA_TRY(cudaMemcpyAsync(scratch, soff.data(), n * 8, cudaMemcpyHostToDevice, stream));
+    SWC_CUDA_TRY(cudaStreamSynchronize(stream));     // soff lives on this stack frame
+    bzip2::Args a;
+    a.in_base = in_base; a.in_off = in_off; a.in_len = in_len;
+    a.out_base = out_base; a.out_off = out_off; a.out_cap = out_cap;
+    a.out_len = out_len; a.consumed_bits = consumed_bits; a.status = status; a.n = n;
+    a.scratch = (u8 *)scratch; a.scr_off = (const u64 *)scratch;
+    return bzip2::launch(a, stream);
+}
+
+// one stream starting at byte `start` of d_in; output grows until it fits
+int bzip2_unit_device(const u8 *d_in, size_t in_len, size_t start, UnitResult &r) {
+    size_t cap = (in_len - start) * 16 + (1u << 20);
+    DevBuf meta;
+    int st = meta.alloc(256);
+    if (st) return st;
+    for (int attempt = 0; attempt < 8; attempt++) {
+        cap = round16(cap);
+        if ((st = r.out.alloc(cap))) return st;
+        u64 h[6] = {start, in_len - start, 0, cap, 0, 0};
+        SWC_CUDA_TRY(cudaMemcpy(meta.p, h, sizeof(h), cudaMemcpyHostToDevice));
+        u64 *m = meta.as<u64>();
+        if ((st = bzip2_batch_impl(d_in, m + 0, m + 1, r.out.as<u8>(), m + 2, m + 3, m + 4, m + 5, (int32_t *)((u8 *)meta.p + 48), 1, 0))) return st;
+        SWC_CUDA_TRY(cudaStreamSynchronize(0));
+        u64 res[7];
+        SWC_CUDA_TRY(cudaMemcpy(res, meta.p, 56, cudaMemcpyDeviceToHost));
+        r.out_len = (size_t)res[4];
+        r.consumed = (size_t)res[5];
+        int32_t st32; memcpy(&st32, &res[6], 4);
+        r.status = st32;
+        if (r.status != SWC_ERR_OUTPUT_OVERFLOW || cap >= ((size_t)1 << 32)) break;
+        cap *= 4;                     // BZip2 cannot report the final size before it has decoded everything
+    }
+    return SWC_OK;
+}
+
+int upload(DevBuf &d, const uint8_t *in, size_t n) {
+    int st = d.alloc(round16(n) + 256);
+    if (st) return st;
+    if (n) SWC_CUDA_TRY(cudaMemcpy(d.p, in, n, cudaMemcpyHostToDevice));
+    return SWC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t swc_bzip2_decompress_batch(const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len,
+                                   uint8_t *out_base, const uint64_t *out_off, const uint64_t *out_cap,
+                                   uint64_t *out_len, uint64_t *consumed_bits, int32_t *status,
+                                   uint64_t n, void *cuda_stream) {
+    if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    return bzip2_batch_impl(in_base, in_off, in_len, out_base, out_off, out_cap, out_len, consumed_bits, status, n, (cudaStream_t)cuda_stream);
+}
+
+// BZip2.decompress(data:) BZip2.swift:22-26 (+ reader form :50)
+int32_t swc_bzip2_decompress(const uint8_t *in, size_t in_len, size_t start_bit,
+                             uint8_t **out, size_t *out_len, size_t *consumed_bits) {
+    if (!out || !out_len) return SWC_ERR_INVALID_ARG;
+    *out = nullptr; *out_len = 0;
+    if (consumed_bits) *consumed_bits = 0;
+    if (start_bit & 7) return SWC_ERR_UNSUPPORTED;      // the reference's byte reads require an aligned reader (BZip2.swift:59)
+    if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    DevBuf d_in;
+    int st = upload(d_in, in, in_len);
+    if (st) return st;
+    UnitResult r;
+    if ((st = bzip2_unit_device(d_in.as<u8>(), in_len, start_bit >> 3, r))) return st;
+    if (consumed_bits) *consumed_bits = r.consumed;
+    if (r.status != SWC_OK && r.status != SWC_BZIP2_WRONG_CRC) return r.status;
+    if ((st = to_host_alloc(r.out.p, r.out_len, out, out_len))) return st;
+    return r.status;
+}
+
+// BZip2.multiDecompress(data:) BZip2.swift:40-48
+int32_t swc_bzip2_multi_decompress(const uint8_t *in, size_t in_len,
+                                   uint8_t **out, size_t *out_len, size_t **stream_ends, size_t *n_streams) {
+    if (!out || !out_len || !stream_ends || !n_streams) return SWC_ERR_INVALID_ARG;
+    *out = nullptr; *out_len = 0; *stream_ends = nullptr; *n_streams = 0;
+    if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    DevBuf d_in;
+    int st = upload(d_in, in, in_len);
+    if (st) return st;
+    std::vector<uint8_t> o;
+    std::vector<size_t> ends;
+    size_t off = 0;
+    int result = SWC_OK;
+    while (off < in_len) {                               // !reader.isFinished
+        UnitResult r;
+        if ((st = bzip2_unit_device(d_in.as<u8>(), in_len, off, r))) return st;
+        if (r.status != SWC_OK && r.status != SWC_BZIP2_WRONG_CRC) return r.status;
+        size_t base = o.size();
+        if (r.status == SWC_BZIP2_WRONG_CRC) { o.clear(); ends.clear(); base = 0; }   // payload = the failing archive only
+        o.resize(base + r.out_len);
+        if (r.out_len) SWC_CUDA_TRY(cudaMemcpy(o.data() + base, r.out.p, r.out_len, cudaMemcpyDeviceToHost));
+        ends.push_back(o.size());
+        if (r.status) { result = r.status; break; }
+        off += (r.consumed + 7) / 8;                     // reader.align()
+    }
+    uint8_t *h = (uint8_t *)swc_alloc(o.size());
+    if (!h) return SWC_ERR_OUTPUT_OVERFLOW;
+    if (!o.empty()) memcpy(h, o.data(), o.size());
+    *out = h; *out_len = o.size();
+    *stream_ends = (size_t *)swc_alloc(sizeof(size_t) * (ends.size() + 1));
+    for (size_t i = 0; i < ends.size(); i++) (*stream_ends)[i] = ends[i];
+    *n_streams = ends.size();
+    return result;
+}
+
+}  // extern "C"

@@ -1,0 +1,439 @@
+// bzip2.cu — batched BZip2 stream decode for sm_100a.  Replaces BZip2.decompress(_: MsbBitReader)
+// (reference Sources/BZip2/BZip2.swift:50-270), BurrowsWheeler.reverse (BurrowsWheeler.swift:29-64) and
+// CheckSums.bzip2crc32 (Sources/Common/CheckSums.swift:30-37).
+//
+// ONE WARP PER UNIT (one .bz2 stream).  The warp executes the bit-serial parts in lock-step (every lane holds the same
+// bit buffer, so control flow is uniform) and uses its 32 lanes where the format allows it:
+//   - the compressed stream is fetched 128 B at a time (one coalesced load, double-buffered), words handed out by shuffle;
+//   - Huffman code length = 1 + popc(ballot(code >= limit[lane])): 20 comparisons in one instruction;
+//   - the 256-entry move-to-front list lives in registers, 8 bytes per lane, and is rotated with one shuffle;
+//   - RUNA/RUNB runs are filled by all lanes; MTF output goes through a 128-byte shared staging line;
+//   - inverse BWT: per-byte histogram -> stable scatter builds the successor array, then the n-step pointer chase is split
+//     over the 32 lanes with the splitter (sparse-ruler) list-ranking trick; RLE1 undo + block CRC run on lane 0.
+#include "common.cuh"
+#include "bzip2.cuh"
+
+namespace swc {
+namespace bzip2 {
+
+constexpr int WARPS = 4;
+constexpr int MAX_SYMS = 258;
+constexpr int MAX_LEN = 20;
+
+struct WarpSmem {
+    u16 syms[6][MAX_SYMS + 2];      // symbols sorted by (length, symbol) per table
+    u32 limit[6][32];               // limit[t][L-1] = left-justified (20-bit) end of the length-L code range; [20..31] = 1<<20
+    u32 base[6][MAX_LEN + 2];       // first left-justified code of length L
+    u16 first[6][MAX_LEN + 2];      // index of the first symbol of length L
+    u8 lens[MAX_SYMS + 2];
+    u8 used[256];
+    u32 counts[256];
+    u32 stage[32];                  // 128-byte output staging line
+    u32 split_next[32], split_len[32];
+};
+
+__constant__ u32 c_bzcrc[256];      // filled by the host at first launch
+
+// ---------------------------------------------------------------- MSB-first bit reader, warp-uniform
+struct Bits {
+    const u8 *base;      // 128-byte aligned chunk base pointer arithmetic is done on (in_base + in_off) & ~127
+    u64 first_chunk;     // absolute chunk index of cur
+    u64 end_byte;        // absolute address one past the unit's last byte
+    u32 cur, nxt;        // this lane's word of the current / next 128-byte chunk (raw little-endian load)
+    int k;               // next word index in cur (0..31)
+    u64 bb;              // left-justified bit buffer
+    int bc;
+    i64 avail;
+    const u32 *chunkp;   // address of the NEXT chunk to prefetch
+
+    __device__ __forceinline__ u32 load_chunk() {
+        const u32 *p = chunkp + lane_id();
+        chunkp += 32;
+        return ((u64)(uintptr_t)p < end_byte) ? __ldg(p) : 0u;
+    }
+    __device__ void init(const u8 *p, u64 len) {
+        uintptr_t a = (uintptr_t)p;
+        end_byte = (u64)a + len;
+        chunkp = (const u32 *)(a & ~(uintptr_t)127);
+        cur = load_chunk();
+        nxt = load_chunk();
+        k = (int)((a & 127) >> 2);
+        bb = 0; bc = 0;
+        avail = (i64)len * 8;
+        refill();
+        const int drop = (int)(a & 3) * 8;
+        bb <<= drop; bc -= drop;
+        need32();
+    }
+    __device__ __forceinline__ void refill() {           // requires bc <= 32
+        u32 w = __shfl_sync(SWC_FULL, cur, k);
+        w = __byte_perm(w, 0, 0x0123);                   // big-endian: first byte in memory = most significant
+        bb |= (u64)w << (32 - bc);
+        bc += 32;
+        if (++k == 32) { cur = nxt; nxt = load_chunk(); k = 0; }
+    }
+    __device__ __forceinline__ void need32() { if (bc <= 32) refill(); }
+    __device__ __forceinline__ u32 peek(int n) const { return n ? (u32)(bb >> (64 - n)) : 0; }
+    __device__ __forceinline__ void skip(int n) { bb <<= n; bc -= n; avail -= n; }
+    __device__ __forceinline__ u32 get(int n) { need32(); u32 v = peek(n); skip(n); return v; }   // n <= 32
+};
+
+// ---------------------------------------------------------------- register-resident MTF list (8 bytes per lane)
+__device__ __forceinline__ u32 mtf_front(u64 v) { return (u32)__shfl_sync(SWC_FULL, (u32)v, 0) & 0xFF; }
+// move element at index i (0..255) to the front; returns it
+__device__ __forceinline__ u32 mtf_move(u64 &v, u32 i) {
+    const u32 lane = lane_id();
+    const u32 q = i >> 3, r = i & 7;
+    const u32 lo = (u32)v, hi = (u32)(v >> 32);
+    const u32 src = r < 4 ? __shfl_sync(SWC_FULL, lo, q) : __shfl_sync(SWC_FULL, hi, q);
+    const u32 e = (src >> ((r & 3) * 8)) & 0xFF;
+    const u32 prev_top = __shfl_up_sync(SWC_FULL, hi, 1) >> 24;          // byte 7 of the previous lane
+    const u64 carry = lane == 0 ? (u64)e : (u64)prev_top;
+    if (lane < q) {
+        v = (v << 8) | carry;
+    } else if (lane == q) {
+        const u64 keep_mask = r == 7 ? 0ull : (~0ull << ((r + 1) * 8));  // bytes above r stay
+        const u64 low = (v << 8) | carry;                                 // bytes 0..r shifted up by one
+        v = (v & keep_mask) | (low & ~keep_mask);
+    }
+    return e;
+}
+
+// ---------------------------------------------------------------- output of the MTF stage (BWT bytes) via staging line
+struct BwtOut {
+    u8 *bwt; u64 cap; u64 n; u32 fill;   // fill = bytes in the staging line
+    WarpSmem *S;
+    __device__ __forceinline__ void flush() {
+        if (fill) {
+            __syncwarp();
+            const u32 lane = lane_id();
+            u64 pos = n - fill;                       // staging line always starts 4-byte aligned in bwt (n-fill % 4 == 0)
+            if (lane * 4 < fill && pos + lane * 4 + 4 <= cap + 3) *(u32 *)(bwt + pos + lane * 4) = S->stage[lane];
+            __syncwarp();
+            fill = 0;
+        }
+    }
+    __device__ __forceinline__ void put(u32 byte) {
+        if (lane_id() == 0) ((u8 *)S->stage)[fill] = (u8)byte;
+        fill++; n++;
+        if (fill == 128) flush();
+    }
+    __device__ void run(u32 byte, u64 count) {
+        // top the staging line up to a 4-byte boundary, flush, then fill wide
+        while (count && (fill & 3)) { put(byte); count--; }
+        if (count >= 4) {                     // fill is a multiple of 4 here, so the flush keeps n word-aligned
+            flush();
+            const u32 lane = lane_id();
+            const u32 w = byte * 0x01010101u;
+            u64 words = count >> 2;
+            if (n + count <= cap) for (u64 i = lane; i < words; i += 32) *(u32 *)(bwt + n + i * 4) = w;
+            n += words * 4;
+            count -= words * 4;
+            __syncwarp();
+        }
+        while (count) { put(byte); count--; }
+    }
+};
+
+// ---------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(WARPS * 32) bzip2_kernel(Args a) {
+    __shared__ WarpSmem smem[WARPS];
+    const u32 lane = lane_id(), warp = threadIdx.x >> 5;
+    const u64 unit = (u64)blockIdx.x * WARPS + warp;
+    if (unit >= a.n) return;
+    WarpSmem &S = smem[warp];
+    const u64 cap = a.out_cap[unit];
+    u8 *out = a.out_base + a.out_off[unit];
+    // per-unit scratch: bwt bytes [scr_cap] | successor array u32 [scr_cap] | selectors u8 [32768]
+    const u64 scr_cap = (cap + 3) & ~3ull;
+    u8 *scr = a.scratch + a.scr_off[unit];
+    u8 *bwt = scr;
+    u32 *succ = (u32 *)(scr + scr_cap + 16);
+    u8 *selectors = (u8 *)(succ + scr_cap) + 16;
+
+    Bits br;
+    br.init(a.in_base + a.in_off[unit], a.in_len[unit]);
+    const i64 total_bits = br.avail;
+    int status = SWC_OK;
+    u64 op = 0;
+    u32 total_crc = 0;
+#define FAIL(c) do { status = (c); goto done; } while (0)
+
+    if (br.avail < 32) FAIL(SWC_BZIP2_WRONG_MAGIC);                                  // BZip2.swift:53
+    if (br.get(16) != 0x425A) FAIL(SWC_BZIP2_WRONG_MAGIC);                           // 'B','Z' (uint16() == 0x5a42 LE)
+    if (br.get(8) != 104) FAIL(SWC_BZIP2_WRONG_VERSION);
+    { u32 bs = br.get(8); if (bs < 0x31 || bs > 0x39) FAIL(SWC_BZIP2_WRONG_BLOCK_SIZE); }
+
+    for (;;) {
+        if (br.avail < 80) FAIL(SWC_BZIP2_WRONG_MAGIC);                              // :71
+        const u64 magic = ((u64)br.get(24) << 24) | br.get(24);
+        const u32 block_crc = br.get(32);
+        if (magic == 0x177245385090ull) {
+            if (total_crc != block_crc) FAIL(SWC_BZIP2_WRONG_CRC);                   // :86
+            break;
+        }
+        if (magic != 0x314159265359ull) FAIL(SWC_BZIP2_WRONG_BLOCK_TYPE);
+
+        // ------------------------------------------------ decode(_:_:) BZip2.swift:97-270
+        if (br.avail < 41) FAIL(SWC_BZIP2_WRONG_MAGIC);
+        if (br.get(1) != 0) FAIL(SWC_BZIP2_RANDOMIZED_BLOCK);
+        const u32 orig_ptr = br.get(24);
+        const u32 used_map = br.get(16);
+        if (br.avail < (i64)(16 * __popc(used_map) + 18)) FAIL(SWC_BZIP2_WRONG_MAGIC);
+        int nused = 0;
+        for (int blk = 0; blk < 16; blk++) {
+            if (used_map & (0x8000u >> blk)) {
+                const u32 m = br.get(16);
+                if (lane == 0) for (int s = 0; s < 16; s++) if (m & (0x8000u >> s)) S.used[nused + __popc(m >> (16 - s))] = (u8)(blk * 16 + s);
+                nused += __popc(m);
+            }
+        }
+        __syncwarp();
+        const int used_count = nused + 2;
+        u64 mtf = 0;                                  // lane l holds list entries 8l..8l+7
+        for (int k = 0; k < 8; k++) { int idx = lane * 8 + k; if (idx < nused) mtf |= (u64)S.used[idx] << (8 * k); }
+        const int ntab = (int)br.get(3);
+        if (ntab < 2 || ntab > 6) FAIL(SWC_BZIP2_WRONG_HUFFMAN_GROUPS);
+        const int nsel = (int)br.get(15);
+        {                                             // selectors :155-173 (MTF over table indices, in a register)
+            u32 tm = 0x543210;                        // nibble k = table index at MTF position k
+            for (int i = 0; i < nsel; i++) {
+                int c = 0;
+                while (br.avail > 0) { u32 b = br.get(1); if (b == 0) break; c++; }
+                if (c >= ntab) FAIL(SWC_BZIP2_WRONG_SELECTOR);
+                const u32 el = (tm >> (4 * c)) & 0xF;
+                const u32 below = tm & ((1u << (4 * c)) - 1);
+                tm = (tm & ~((1u << (4 * (c + 1))) - 1)) | (below << 4) | el;
+                if (lane == 0) selectors[i] = (u8)el;
+            }
+        }
+        for (int t = 0; t < ntab; t++) {              // code lengths :177-203
+            if (br.avail < 5) FAIL(SWC_BZIP2_WRONG_HUFFMAN_CODE_LENGTH);
+            int length = (int)br.get(5);
+            for (int i = 0; i < used_count; i++) {
+                if (length < 0 || length > 20) FAIL(SWC_BZIP2_WRONG_HUFFMAN_CODE_LENGTH);
+                while (br.avail > 0) {
+                    if (br.get(1) == 0) break;
+                    if (br.avail <= 0) FAIL(SWC_BZIP2_WRONG_HUFFMAN_CODE_LENGTH);
+                    length -= (int)br.get(1) * 2 - 1;
+                }
+                if (i == used_count - 1 && length > 20) FAIL(SWC_ERR_REFERENCE_TRAP);   // unbounded tree in the reference
+                if (lane == 0) S.lens[i] = (u8)(length < 0 ? 0 : length);
+            }
+            __syncwarp();
+            // canonical tables (Code.huffmanCodes + DecodingTree semantics for Kraft <= 1)
+            u32 code = 0, idx = 0;
+            bool over = false;
+            for (int L = 1; L <= MAX_LEN; L++) {
+                if (lane == 0) { S.base[t][L] = code; S.first[t][L] = (u16)idx; }
+                for (int s = 0; s < used_count; s++) {
+                    if (S.lens[s] == L) {
+                        if (code >= (1u << 20)) over = true;
+                        if (lane == 0) S.syms[t][idx] = (u16)s;
+                        idx++;
+                        code += 1u << (20 - L);
+                    }
+                }
+                if (lane == 0) S.limit[t][L - 1] = code > (1u << 20) ? (1u << 20) : code;
+            }
+            if (lane == 0) for (int L = MAX_LEN; L < 32; L++) S.limit[t][L] = 1u << 20;
+            if (over) FAIL(SWC_ERR_UNSUPPORTED);      // over-subscribed set (heap-overwrite semantics): not taken by this kernel
+            __syncwarp();
+        }
+        __syncwarp();
+        if (nsel == 0) FAIL(SWC_ERR_REFERENCE_TRAP);                                 // selectors[0]
+
+        // ------------------------------------------------ symbol loop :212-246
+        BwtOut bo; bo.bwt = bwt; bo.cap = scr_cap; bo.n = 0; bo.fill = 0; bo.S = &S;
+        {
+            int decoded = 0, sel_idx = 1;
+            int table = selectors[0];
+            u32 my_limit = S.limit[table][lane];
+            u64 run_length = 0, repeat_power = 1;
+            for (;;) {
+                if (decoded >= 50) {
+                    if (sel_idx >= nsel) FAIL(SWC_BZIP2_WRONG_SELECTOR);
+                    table = selectors[sel_idx++];
+                    my_limit = S.limit[table][lane];
+                    decoded = 0;
+                }
+                br.need32();
+                const u32 r20 = br.peek(20);
+                const int L = 1 + __popc(__ballot_sync(SWC_FULL, r20 >= my_limit));
+                if (L > MAX_LEN || br.avail < L) FAIL(SWC_BZIP2_SYMBOL_NOT_FOUND);
+                const u32 sidx = S.first[table][L] + ((r20 - S.base[table][L]) >> (20 - L));
+                const int symbol = S.syms[table][sidx];
+                br.skip(L);
+                decoded++;
+                if (symbol < 2) {                                                    // RUNA / RUNB :226-230
+                    run_length += repeat_power << symbol;
+                    repeat_power <<= 1;
+                    continue;
+                }
+                if (run_length > 0) {
+                    if (nused == 0) FAIL(SWC_ERR_REFERENCE_TRAP);
+                    if (bo.n + run_length > scr_cap) { bo.n += run_length; FAIL(SWC_ERR_OUTPUT_OVERFLOW); }
+                    bo.run(mtf_front(mtf), run_length);
+                    run_length = 0; repeat_power = 1;
+                }
+                if (symbol == used_count - 1) break;                                 // EOB :239
+                if (bo.n + 1 > scr_cap) FAIL(SWC_ERR_OUTPUT_OVERFLOW);
+                bo.put(mtf_move(mtf, (u32)symbol - 1));                              // :243-245
+            }
+            // pad the staging line so the final flush writes whole words
+            bo.flush();
+        }
+        {
+            // ------------------------------------------------ BurrowsWheeler.reverse
+            const u64 n = bo.n;
+            __syncwarp();
+            if (n > 0) {
+                if (orig_ptr >= n) FAIL(SWC_ERR_REFERENCE_TRAP);
+                // histogram (per-lane partial counts folded through shared atomics)
+                for (int c = lane; c < 256; c += 32) S.counts[c] = 0;
+                __syncwarp();
+                for (u64 i = lane; i < n; i += 32) atomicAdd(&S.counts[bwt[i]], 1u);
+                __syncwarp();
+                // exclusive scan of 256 counters: 8 per lane
+                u32 loc[8], sum = 0;
+                for (int k = 0; k < 8; k++) { loc[k] = S.counts[lane * 8 + k]; sum += loc[k]; }
+                u32 incl = sum;
+                for (int d = 1; d < 32; d <<= 1) { u32 v = __shfl_up_sync(SWC_FULL, incl, d); if (lane >= (u32)d) incl += v; }
+                u32 run = incl - sum;
+                for (int k = 0; k < 8; k++) { S.counts[lane * 8 + k] = run; run += loc[k]; }
+                __syncwarp();
+                // stable scatter: successor[base[c]++] = i, in increasing i — 32 positions per round, ranked with match_any
+                for (u64 i0 = 0; i0 < n; i0 += 32) {
+                    const u64 i = i0 + lane;
+                    const bool act = i < n;
+                    const u32 c = act ? bwt[i] : 0x100 + lane;
+                    const u32 peers = __match_any_sync(SWC_FULL, c);
+                    const u32 rank = __popc(peers & ((1u << lane) - 1));
+                    if (act) succ[S.counts[c] + rank] = (u32)i;
+                    __syncwarp();
+                    if (act && rank == 0) S.counts[c] += __popc(peers);
+                    __syncwarp();
+                }
+                __syncwarp();
+                // ---- pointer chase split over 32 lanes (splitter list ranking) ----
+                // splitter j starts at index s_j (s_0 = orig_ptr); bit 31 of succ[s_j] marks it.
+                const u32 MARK = 0x80000000u;
+                u32 my_start = lane == 0 ? orig_ptr : (u32)(((u64)lane * n) / 32);
+                // lanes whose start collides with an earlier lane's start sit out
+                bool owner = true;
+                for (int j = 0; j < 32; j++) { u32 sj = __shfl_sync(SWC_FULL, my_start, j); if (j < (int)lane && sj == my_start) owner = false; }
+                if (owner) S.split_len[lane] = 0;
+                __syncwarp();
+                if (owner) atomicOr(&succ[my_start], MARK);
+                __syncwarp();
+                // walk 1: length of my segment and which splitter ends it
+                u32 seg_len = 0, end_at = 0;
+                if (owner) {
+                    u32 cur = my_start;
+                    do { cur = succ[cur] & ~MARK; seg_len++; } while (!(succ[cur] & MARK) && seg_len < n);
+                    end_at = cur;
+                }
+                // map end index -> owning lane
+                u32 next_lane = 0xFFFFFFFFu;
+                for (int j = 0; j < 32; j++) {
+                    u32 sj = __shfl_sync(SWC_FULL, my_start, j);
+                    bool oj = __shfl_sync(SWC_FULL, (u32)owner, j) != 0;
+                    if (owner && oj && sj == end_at && next_lane == 0xFFFFFFFFu) next_lane = j;
+                }
+                // lane 0 order: follow segments from splitter 0 assigning output offsets until n bytes are covered
+                // (the path from orig_ptr is a cycle of length C <= n; when C < n the output wraps around it)
+                u64 my_off = ~0ull, cycle = 0;
+                {
+                    u32 curl = 0; u64 off = 0;
+                    for (int step = 0; step < 32; step++) {
+                        const u32 sl = __shfl_sync(SWC_FULL, seg_len, curl);
+                        const u32 nl = __shfl_sync(SWC_FULL, next_lane, curl);
+                        if (lane == curl && my_off == ~0ull) my_off = off;
+                        off += sl;
+                        if (nl == 0 || nl == 0xFFFFFFFFu) { cycle = off; break; }
+                        curl = nl;
+                        if (step == 31) cycle = off;
+                    }
+                }
+                cycle = __shfl_sync(SWC_FULL, cycle, 0);
+                // walk 2: emit my segment at my_off (+ k*cycle while < n). Output of this stage overwrites nothing it reads:
+                // it goes to `out + op` region?  No — RLE1 still has to expand it, so it is written back over... a second buffer:
+                // the low half of the successor array is dead after the walk, so the text goes to `text` = (u8*)succ + 4n.
+                // (scr layout keeps 4*scr_cap bytes there; text needs n <= scr_cap bytes placed after the live entries.)
+                u8 *text = selectors + 32768 + 16;
+                if (owner && my_off != ~0ull) {
+                    u32 cur = my_start;
+                    for (u32 k = 0; k < seg_len; k++) {
+                        cur = succ[cur] & ~MARK;
+                        const u8 ch = bwt[cur];
+                        for (u64 pos = my_off + k; pos < n; pos += cycle) text[pos] = ch;
+                    }
+                }
+                __syncwarp();
+                // ------------------------------------------------ RLE1 undo + block CRC (lane 0) :251-267
+                u32 crc = 0xFFFFFFFFu;
+                u64 bop = op;
+                if (lane == 0) {
+                    u64 i = 0;
+                    while (i < n) {
+                        const u8 c0 = text[i];
+                        if (n >= 4 && i < n - 4 && c0 == text[i + 1] && c0 == text[i + 2] && c0 == text[i + 3]) {
+                            const u32 runl = (u32)text[i + 4] + 4;
+                            for (u32 k = 0; k < runl; k++) {
+                                if (bop < cap) out[bop] = c0;
+                                bop++;
+                                crc = (crc << 8) ^ c_bzcrc[((crc >> 24) ^ c0) & 0xFF];
+                            }
+                            i += 5;
+                        } else {
+                            if (bop < cap) out[bop] = c0;
+                            bop++;
+                            crc = (crc << 8) ^ c_bzcrc[((crc >> 24) ^ c0) & 0xFF];
+                            i += 1;
+                        }
+                    }
+                }
+                bop = __shfl_sync(SWC_FULL, (u32)bop, 0) | ((u64)__shfl_sync(SWC_FULL, (u32)(bop >> 32), 0) << 32);
+                crc = ~__shfl_sync(SWC_FULL, crc, 0);
+                op = bop;
+                if (op > cap) FAIL(SWC_ERR_OUTPUT_OVERFLOW);
+                if (crc != block_crc) FAIL(SWC_BZIP2_WRONG_CRC);                         // :81 (payload includes this block)
+            } else {
+                if (block_crc != 0) FAIL(SWC_BZIP2_WRONG_CRC);                           // crc of the empty block is 0
+            }
+        }
+        total_crc = ((total_crc << 1) | (total_crc >> 31)) ^ block_crc;                  // :83-84
+    }
+done:
+#undef FAIL
+    if (lane == 0) {
+        a.out_len[unit] = op;
+        a.consumed_bits[unit] = (u64)(total_bits - br.avail);
+        a.status[unit] = status;
+    }
+}
+
+static bool g_crc_ready = false;
+
+size_t scratch_per_unit(u64 cap) {
+    const u64 scr_cap = (cap + 3) & ~3ull;
+    // bwt | succ (u32) | selectors | text
+    return (size_t)(scr_cap + 16 + scr_cap * 4 + 16 + 32768 + 16 + scr_cap + 256 + 255) & ~(size_t)255;
+}
+
+int launch(const Args &a, cudaStream_t stream) {
+    if (a.n == 0) return SWC_OK;
+    if (!g_crc_ready) {
+        u32 tab[256];
+        for (u32 i = 0; i < 256; i++) { u32 c = i << 24; for (int k = 0; k < 8; k++) c = (c & 0x80000000u) ? (c << 1) ^ 0x04C11DB7u : c << 1; tab[i] = c; }
+        SWC_CUDA_TRY(cudaMemcpyToSymbol(c_bzcrc, tab, sizeof(tab)));
+        g_crc_ready = true;
+    }
+    bzip2_kernel<<<(unsigned)((a.n + WARPS - 1) / WARPS), WARPS * 32, 0, stream>>>(a);
+    count_launch();
+    SWC_CUDA_TRY(cudaGetLastError());
+    return SWC_OK;
+}
+
+}  // namespace bzip2
+}  // namespace swc

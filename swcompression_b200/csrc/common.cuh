@@ -40,6 +40,9 @@ int cuda_fail(cudaError_t e, const char *where);
         if (_e != cudaSuccess) return swc::cuda_fail(_e, #expr);               \
     } while (0)
 
+// optional per-kernel timing: when enabled, launchers drop a CUDA event on `stream` between their kernels
+void timing_mark(cudaStream_t stream);
+
 // scratch pool: grow-only per-device buffer, used when the caller passes no scratch
 int scratch_get(size_t bytes, void **p, cudaStream_t stream);
 

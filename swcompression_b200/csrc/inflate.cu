@@ -21,14 +21,17 @@ namespace swc {
 namespace inflate {
 
 // ---- per-lane shared-memory layout (32-bit words; word w of lane l lives at warp_base[w * 32 + l]) ----
-constexpr int W_LIT_SYM = 0;     // 288 x u16 : lit/len symbols sorted by (code length, symbol)
-constexpr int W_DST_SYM = 144;   // 32 x u8   : distance symbols sorted likewise
-constexpr int W_LIT_BO = 152;    // [1..15]   : first left-justified 15-bit code of length L | index of its first symbol << 16
-constexpr int W_DST_BO = 168;
-constexpr int W_CL_SYM = 184;    // 19 x u8   : code-length-alphabet symbols, sorted
-constexpr int W_CL_BO = 189;     // [1..7]
-constexpr int W_TOTAL = 197;
+constexpr int W_LIT_SYM = 0;     // 288 x u8  : low byte of the lit/len symbols sorted by (code length, symbol)
+constexpr int W_LIT_HI = 72;     // 288 bits  : bit i set = sorted symbol i is >= 256 (EOB / length symbol)
+constexpr int W_DST_SYM = 81;    // 32 x u8   : distance symbols sorted likewise
+constexpr int W_LIT_BO = 89;     // [1..15]   : first left-justified 15-bit code of length L | index of its first symbol << 16
+constexpr int W_DST_BO = 105;
+constexpr int W_CL_SYM = 121;    // 19 x u8   : code-length-alphabet symbols, sorted
+constexpr int W_CL_BO = 126;     // [1..7]
+constexpr int W_TOTAL = 134;     // 536 B per lane -> 12 resident warps per SM
 constexpr int WARPS_PER_CTA = 4;
+constexpr int CTAS_PER_SM = 3;
+constexpr int KLIT = 4;          // lit/len symbols a lane may decode per round before the warp services pending matches
 constexpr int SMEM_LUT_WORDS = 64;   // CTA-shared length/distance base+extra tables
 constexpr size_t SMEM_BYTES = (size_t)WARPS_PER_CTA * W_TOTAL * 32 * 4 + SMEM_LUT_WORDS * 4;
 
@@ -50,33 +53,29 @@ struct Limits {
 
 // ------------------------------------------------------------------------------------------------ bit reader
 struct BitReader {
-    const uint4 *p, *pend;
-    uint4 cur, nxt;
-    int k;        // next 32-bit word of `cur`
-    u64 bb;       // bit buffer, LSB first
-    int bc;       // valid bits in bb
-    i64 avail;    // the reference's bitsLeft: real input bits not yet consumed
+    const u32 *p, *pend;   // next 32-bit word to prefetch / first word past the unit
+    u32 wnext;             // prefetched word (loaded one refill ahead, so its latency is off the decode chain)
+    u64 bb;                // bit buffer, LSB first
+    int bc;                // valid bits in bb
+    i64 avail;             // the reference's bitsLeft: real input bits not yet consumed
 
-    __device__ __forceinline__ uint4 fetch() {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (p < pend) v = ld_stream16(p);
+    __device__ __forceinline__ u32 fetch() {
+        u32 v = 0;
+        if (p < pend) v = __ldg(p);
         p++;
         return v;
     }
     __device__ __forceinline__ void refill() {   // requires bc <= 32
-        u32 w = k == 0 ? cur.x : k == 1 ? cur.y : k == 2 ? cur.z : cur.w;
-        bb |= (u64)w << bc;
+        bb |= (u64)wnext << bc;
         bc += 32;
-        if (++k == 4) { cur = nxt; k = 0; nxt = fetch(); }
+        wnext = fetch();
     }
     __device__ __forceinline__ void need32() { if (bc <= 32) refill(); }
     __device__ void init(const u8 *base, u64 off, u64 len, u32 bitskip) {
         uintptr_t a = (uintptr_t)(base + off);
-        p = (const uint4 *)(a & ~(uintptr_t)15);
-        pend = (const uint4 *)((a + len + 15) & ~(uintptr_t)15);
-        cur = fetch();
-        nxt = fetch();
-        k = (int)((a & 15) >> 2);
+        p = (const u32 *)(a & ~(uintptr_t)3);
+        pend = (const u32 *)((a + len + 3) & ~(uintptr_t)3);
+        wnext = fetch();
         bb = 0; bc = 0;
         refill();
         u32 drop = (u32)(a & 3) * 8 + bitskip;    // < 32
@@ -198,7 +197,8 @@ __device__ __forceinline__ int static_len(int i) {   // i < 288: lit/len, else d
     return i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5;
 }
 
-template <typename SymT>
+// KIND 0: lit/len alphabet (u8 table + high-bit vector), KIND 1: u8 table (distance / code-length alphabets)
+template <int KIND>
 __device__ __forceinline__ int decode_symbol(BitReader &br, const Limits &lim, const u32 *bo, const u32 *symw, int &len_out) {
     u32 r15 = __brev(br.peek(15)) >> 17;
     int L = code_length(r15, lim);
@@ -206,8 +206,12 @@ __device__ __forceinline__ int decode_symbol(BitReader &br, const Limits &lim, c
     if (L > 15) return -1;
     u32 w = bo[L * 32];
     u32 idx = (w >> 16) + ((r15 - (w & 0xFFFFu)) >> (15 - L));
-    if (sizeof(SymT) == 2) return ((const u16 *)(symw + (idx >> 1) * 32))[idx & 1];
-    return ((const u8 *)(symw + (idx >> 2) * 32))[idx & 3];
+    u32 lo = ((const u8 *)(symw + (idx >> 2) * 32))[idx & 3];
+    if (KIND == 0) {
+        u32 hw = symw[(W_LIT_HI - W_LIT_SYM + (idx >> 5)) * 32];
+        lo |= ((hw >> (idx & 31)) & 1u) << 8;
+    }
+    return (int)lo;
 }
 
 // One pass over the code lengths. PASS 0 counts lengths into the BO areas, PASS 1 scatters symbols into the sorted
@@ -223,7 +227,7 @@ __device__ int run_lengths(BitReader &br, u32 *S, const Limits &cl_lim, bool dyn
         } else {
             br.need32();
             int cl;
-            int sym = decode_symbol<u8>(br, cl_lim, S + W_CL_BO * 32, S + W_CL_SYM * 32, cl);
+            int sym = decode_symbol<1>(br, cl_lim, S + W_CL_BO * 32, S + W_CL_SYM * 32, cl);
             if (sym < 0 || br.avail < cl) return SWC_DEFLATE_SYMBOL_NOT_FOUND;
             br.skip(cl);
             if (sym <= 15) {
@@ -256,8 +260,12 @@ __device__ int run_lengths(BitReader &br, u32 *S, const Limits &cl_lim, bool dyn
                     u32 w = bo[len * 32];
                     bo[len * 32] = w + 0x10000u;
                     u32 pos = w >> 16;
-                    if (is_lit) ((u16 *)(S + (W_LIT_SYM + (pos >> 1)) * 32))[pos & 1] = (u16)n;
-                    else ((u8 *)(S + (W_DST_SYM + (pos >> 2)) * 32))[pos & 3] = (u8)(n - hlit);
+                    if (is_lit) {
+                        ((u8 *)(S + (W_LIT_SYM + (pos >> 2)) * 32))[pos & 3] = (u8)n;
+                        if (n >= 256) S[(W_LIT_HI + (pos >> 5)) * 32] |= 1u << (pos & 31);
+                    } else {
+                        ((u8 *)(S + (W_DST_SYM + (pos >> 2)) * 32))[pos & 3] = (u8)(n - hlit);
+                    }
                 }
             }
         }
@@ -268,7 +276,138 @@ __device__ int run_lengths(BitReader &br, u32 *S, const Limits &cl_lim, bool dyn
 }
 
 // ------------------------------------------------------------------------------------------------ K1
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 2)
+// Control flow is a per-lane state machine driven by ONE warp-wide loop: every round starts with a full-mask vote,
+// which forces the 32 lanes back into lock-step.  (A plain per-lane `for(;;)` with early exits lets independent thread
+// scheduling split the warp into sub-groups that never re-converge: measured 50x slower.)
+// A round = up to KLIT lit/len symbols per lane, then ONE pass of the (long) match path for every lane that has a
+// length symbol pending — so the match instructions are issued with many lanes active instead of ~15 % of them.
+enum { ST_HEADER = 0, ST_SYMBOLS = 1, ST_MATCH = 2, ST_DONE = 3 };
+
+struct BlockCtx {
+    Limits lit_lim, dst_lim;
+    bool is_last;
+};
+
+// Block header (Deflate.swift:41-168): stored blocks are copied here; for Huffman blocks the per-lane tables are built.
+// Returns SWC_OK or the reference's error; `next` receives the state to continue in.
+__device__ __forceinline__ int begin_block(BitReader &br, Emitter &em, u32 *S, BlockCtx &bc, int &next) {
+    br.need32();
+    if (br.avail < 3) return SWC_ERR_REFERENCE_TRAP;                                    // :41-43 unguarded reads
+    const u32 hdr = br.peek(3); br.skip(3);
+    bc.is_last = (hdr & 1) != 0;
+    const u32 btype = hdr >> 1;
+    if (btype == 3) return SWC_DEFLATE_WRONG_BLOCK_TYPE;                                 // :239
+    if (btype == 0) {                                                                   // :45-65
+        br.skip((int)(br.avail & 7));
+        br.need32();
+        if (br.avail < 32) return SWC_DEFLATE_WRONG_UNCOMPRESSED_BLOCK_LENGTHS;
+        const u32 length = br.peek(16); br.skip(16);
+        br.need32();
+        const u32 nlength = br.peek(16); br.skip(16);
+        if ((length & nlength) != 0) return SWC_DEFLATE_WRONG_UNCOMPRESSED_BLOCK_LENGTHS;
+        if ((br.avail >> 3) < (i64)length) return SWC_DEFLATE_WRONG_UNCOMPRESSED_BLOCK_LENGTHS;
+        for (u32 i = 0; i < length; i++) {
+            br.need32();
+            em.literal(br.peek(8));
+            br.skip(8);
+        }
+        next = bc.is_last ? ST_DONE : ST_HEADER;
+        return SWC_OK;
+    }
+    const bool dynamic = btype == 2;
+    int hlit = 288, hdist = 32;
+    Limits cl_lim;
+    BitReader saved;
+#pragma unroll
+    for (int L = 1; L <= 15; L++) { S[(W_LIT_BO + L) * 32] = 0; S[(W_DST_BO + L) * 32] = 0; }
+#pragma unroll
+    for (int k = 0; k < 9; k++) S[(W_LIT_HI + k) * 32] = 0;
+    if (dynamic) {
+        br.need32();
+        if (br.avail < 14) return SWC_DEFLATE_SYMBOL_NOT_FOUND;
+        hlit = (int)br.peek(5) + 257; br.skip(5);
+        if (hlit > 286) return SWC_DEFLATE_WRONG_SYMBOL;                                 // :94
+        hdist = (int)br.peek(5) + 1; br.skip(5);
+        const int hclen = (int)br.peek(4) + 4; br.skip(4);
+        if (br.avail < 3 * hclen) return SWC_DEFLATE_SYMBOL_NOT_FOUND;
+        u64 cl = 0;                                 // 19 x 3-bit code lengths, indexed by symbol
+        for (int i = 0; i < hclen; i++) {
+            br.need32();
+            cl |= (u64)br.peek(3) << (3 * c_cl_order[i]);
+            br.skip(3);
+        }
+        u64 cnt = 0;                                // 8 x 8-bit counters
+        for (int s = 0; s < 19; s++) cnt += 1ull << (8 * ((cl >> (3 * s)) & 7));
+#pragma unroll
+        for (int L = 1; L <= 7; L++) S[(W_CL_BO + L) * 32] = (u32)(cnt >> (8 * L)) & 0xFF;
+        const u32 kraft = finalize_tables(S + W_CL_BO * 32, cl_lim, 7);
+        if (kraft > 0x8000u) return SWC_INTERNAL_NEEDS_SLOW;
+        for (int s = 0; s < 19; s++) {
+            const u32 l = (u32)(cl >> (3 * s)) & 7;
+            if (l) {
+                const u32 w = S[(W_CL_BO + l) * 32];
+                S[(W_CL_BO + l) * 32] = w + 0x10000u;
+                const u32 pos = w >> 16;
+                ((u8 *)(S + (W_CL_SYM + (pos >> 2)) * 32))[pos & 3] = (u8)s;
+            }
+        }
+        rewind_offsets(S + W_CL_BO * 32, 7);
+        saved = br;
+    }
+    int st = run_lengths<0>(br, S, cl_lim, dynamic, hlit, hdist);
+    if (st) return st;
+    const u32 k1 = finalize_tables(S + W_LIT_BO * 32, bc.lit_lim, 15);
+    const u32 k2 = finalize_tables(S + W_DST_BO * 32, bc.dst_lim, 15);
+    if (k1 > 0x8000u || k2 > 0x8000u) return SWC_INTERNAL_NEEDS_SLOW;
+    if (dynamic) br = saved;
+    run_lengths<1>(br, S, cl_lim, dynamic, hlit, hdist);
+    rewind_offsets(S + W_LIT_BO * 32, 15);
+    rewind_offsets(S + W_DST_BO * 32, 15);
+    next = ST_SYMBOLS;
+    return SWC_OK;
+}
+
+// One lit/len symbol (Deflate.swift:171-198). Literals are emitted; a length symbol reads its extra bits, leaves the
+// match length in `pend_len` and moves the lane to ST_MATCH. Returns SWC_OK or the reference's error.
+__device__ __forceinline__ int litlen_step(BitReader &br, Emitter &em, const u32 *S, const BlockCtx &bc, const u32 *lut,
+                                           int &state, u32 &pend_len) {
+    br.need32();
+    int L;
+    const int sym = decode_symbol<0>(br, bc.lit_lim, S + W_LIT_BO * 32, S + W_LIT_SYM * 32, L);
+    if (sym < 0 || br.avail < L) return SWC_DEFLATE_SYMBOL_NOT_FOUND;
+    br.skip(L);
+    if (sym < 256) { em.literal((u32)sym); return SWC_OK; }
+    if (sym == 256) { state = bc.is_last ? ST_DONE : ST_HEADER; return SWC_OK; }
+    if (sym > 285) return SWC_DEFLATE_WRONG_SYMBOL;
+    const u32 le = lut[sym - 257];
+    const int eb = (int)(le >> 16);
+    if (br.avail < eb) return SWC_DEFLATE_SYMBOL_NOT_FOUND;
+    pend_len = (le & 0xFFFFu) + br.peek(eb);
+    br.skip(eb);
+    state = ST_MATCH;
+    return SWC_OK;
+}
+
+// Distance half of a match (Deflate.swift:199-232).
+__device__ __forceinline__ int dist_step(BitReader &br, Emitter &em, const u32 *S, const BlockCtx &bc, const u32 *lut, u32 length) {
+    br.need32();
+    int DL;
+    const int dsym = decode_symbol<1>(br, bc.dst_lim, S + W_DST_BO * 32, S + W_DST_SYM * 32, DL);
+    if (dsym < 0 || br.avail < DL) return SWC_DEFLATE_SYMBOL_NOT_FOUND;
+    br.skip(DL);
+    if (dsym > 29) return SWC_DEFLATE_WRONG_SYMBOL;
+    const u32 de = lut[32 + dsym];
+    const int db = (int)(de >> 16);
+    if (br.avail < db) return SWC_DEFLATE_SYMBOL_NOT_FOUND;
+    const u32 dist = (de & 0xFFFFu) + br.peek(db);
+    br.skip(db);
+    if (dist > em.op) return SWC_ERR_REFERENCE_TRAP;                                     // :219 negative array index
+    if ((u64)em.op + length > 0xFFFFFFF0ull) return SWC_ERR_UNSUPPORTED;
+    em.match(length, dist);
+    return SWC_OK;
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
 inflate_huffman_kernel(BatchArgs a) {
     extern __shared__ u32 smem[];
     u32 *lut = smem;                                   // [0,32) length table, [32,64) distance table
@@ -278,144 +417,58 @@ inflate_huffman_kernel(BatchArgs a) {
     u32 *S = smem + SMEM_LUT_WORDS + warp * (W_TOTAL * 32) + lane;     // this lane's word 0
 
     const u64 unit = (u64)blockIdx.x * (WARPS_PER_CTA * 32) + threadIdx.x;
-    if (unit >= a.n) return;
-
-    const u64 in_len = a.in_len[unit];
-    const u64 cap64 = a.out_cap[unit];
-    int status = SWC_OK;
+    const bool live = unit < a.n;
+    int status = SWC_OK, state = ST_DONE;
     BitReader br;
     Emitter em;
-    em.out = a.out_base + a.out_off[unit];
-    em.rec = a.rec_base + rec_start(a.out_off[unit]);
-    em.op = 0; em.cap = cap64 > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (u32)cap64;
-    em.last_end = 0; em.nrec = 0; em.acc = 0; em.dirty = false;
-    const u32 bitskip = a.start_bits ? a.start_bits[unit] : 0;
-    if (in_len >= (1ull << 32)) {
-        a.consumed_bits[unit] = 0; a.out_len[unit] = 0; a.rec_count[unit] = 0; a.status[unit] = SWC_ERR_UNSUPPORTED;
-        return;
-    }
-    br.init(a.in_base, a.in_off[unit], in_len, bitskip);
-    {
-        const i64 total_bits = br.avail;
-        Limits lit_lim, dst_lim, cl_lim;
-        if (br.avail < 10) { status = SWC_DEFLATE_WRONG_BLOCK_TYPE; goto done; }            // Deflate.swift:36
-        for (;;) {
-            br.need32();
-            if (br.avail < 3) { status = SWC_ERR_REFERENCE_TRAP; goto done; }               // :41-43 unguarded reads
-            const u32 hdr = br.peek(3); br.skip(3);
-            const u32 is_last = hdr & 1, btype = hdr >> 1;
-            if (btype == 0) {                                                               // :45-65
-                u32 pad = (u32)(br.avail & 7);
-                br.skip(pad);
-                br.need32();
-                if (br.avail < 32) { status = SWC_DEFLATE_WRONG_UNCOMPRESSED_BLOCK_LENGTHS; goto done; }
-                u32 length = br.peek(16); br.skip(16);
-                br.need32();
-                u32 nlength = br.peek(16); br.skip(16);
-                if ((length & nlength) != 0) { status = SWC_DEFLATE_WRONG_UNCOMPRESSED_BLOCK_LENGTHS; goto done; }
-                if ((br.avail >> 3) < (i64)length) { status = SWC_DEFLATE_WRONG_UNCOMPRESSED_BLOCK_LENGTHS; goto done; }
-                for (u32 i = 0; i < length; i++) {
-                    br.need32();
-                    em.literal(br.peek(8));
-                    br.skip(8);
-                }
-            } else if (btype == 3) {
-                status = SWC_DEFLATE_WRONG_BLOCK_TYPE; goto done;                            // :239
-            } else {
-                // ---------------- table construction ----------------
-                const bool dynamic = btype == 2;
-                int hlit = 288, hdist = 32;
-                BitReader saved;
-#pragma unroll
-                for (int L = 1; L <= 15; L++) { S[(W_LIT_BO + L) * 32] = 0; S[(W_DST_BO + L) * 32] = 0; }
-                if (dynamic) {
-                    br.need32();
-                    if (br.avail < 14) { status = SWC_DEFLATE_SYMBOL_NOT_FOUND; goto done; }
-                    hlit = (int)br.peek(5) + 257; br.skip(5);
-                    if (hlit > 286) { status = SWC_DEFLATE_WRONG_SYMBOL; goto done; }       // :94
-                    hdist = (int)br.peek(5) + 1; br.skip(5);
-                    const int hclen = (int)br.peek(4) + 4; br.skip(4);
-                    if (br.avail < 3 * hclen) { status = SWC_DEFLATE_SYMBOL_NOT_FOUND; goto done; }
-                    u64 cl = 0;                         // 19 x 3-bit code lengths, indexed by symbol
-                    for (int i = 0; i < hclen; i++) {
-                        br.need32();
-                        cl |= (u64)br.peek(3) << (3 * c_cl_order[i]);
-                        br.skip(3);
-                    }
-                    u64 cnt = 0;                        // 8 x 8-bit counters
-                    for (int s = 0; s < 19; s++) cnt += 1ull << (8 * ((cl >> (3 * s)) & 7));
-#pragma unroll
-                    for (int L = 1; L <= 7; L++) S[(W_CL_BO + L) * 32] = (u32)(cnt >> (8 * L)) & 0xFF;
-                    u32 kraft = finalize_tables(S + W_CL_BO * 32, cl_lim, 7);
-                    if (kraft > 0x8000u) { status = SWC_INTERNAL_NEEDS_SLOW; goto done; }
-                    for (int s = 0; s < 19; s++) {
-                        u32 l = (u32)(cl >> (3 * s)) & 7;
-                        if (l) {
-                            u32 w = S[(W_CL_BO + l) * 32];
-                            S[(W_CL_BO + l) * 32] = w + 0x10000u;
-                            u32 pos = w >> 16;
-                            ((u8 *)(S + (W_CL_SYM + (pos >> 2)) * 32))[pos & 3] = (u8)s;
-                        }
-                    }
-                    rewind_offsets(S + W_CL_BO * 32, 7);
-                    saved = br;
-                }
-                status = run_lengths<0>(br, S, cl_lim, dynamic, hlit, hdist);
-                if (status) goto done;
-                {
-                    u32 k1 = finalize_tables(S + W_LIT_BO * 32, lit_lim, 15);
-                    u32 k2 = finalize_tables(S + W_DST_BO * 32, dst_lim, 15);
-                    if (k1 > 0x8000u || k2 > 0x8000u) { status = SWC_INTERNAL_NEEDS_SLOW; goto done; }
-                }
-                if (dynamic) br = saved;
-                run_lengths<1>(br, S, cl_lim, dynamic, hlit, hdist);
-                rewind_offsets(S + W_LIT_BO * 32, 15);
-                rewind_offsets(S + W_DST_BO * 32, 15);
-
-                // ---------------- symbol loop (Deflate.swift:171-236) ----------------
-                for (;;) {
-                    br.need32();
-                    int L;
-                    int sym = decode_symbol<u16>(br, lit_lim, S + W_LIT_BO * 32, S + W_LIT_SYM * 32, L);
-                    if (sym < 0 || br.avail < L) { status = SWC_DEFLATE_SYMBOL_NOT_FOUND; goto done; }
-                    br.skip(L);
-                    if (sym < 256) {
-                        em.literal((u32)sym);
-                        continue;
-                    }
-                    if (sym == 256) break;
-                    if (sym > 285) { status = SWC_DEFLATE_WRONG_SYMBOL; goto done; }
-                    const u32 le = lut[sym - 257];
-                    const int eb = (int)(le >> 16);
-                    if (br.avail < eb) { status = SWC_DEFLATE_SYMBOL_NOT_FOUND; goto done; }
-                    const u32 length = (le & 0xFFFFu) + br.peek(eb);
-                    br.skip(eb);
-                    br.need32();
-                    int DL;
-                    int dsym = decode_symbol<u8>(br, dst_lim, S + W_DST_BO * 32, S + W_DST_SYM * 32, DL);
-                    if (dsym < 0 || br.avail < DL) { status = SWC_DEFLATE_SYMBOL_NOT_FOUND; goto done; }
-                    br.skip(DL);
-                    if (dsym > 29) { status = SWC_DEFLATE_WRONG_SYMBOL; goto done; }
-                    const u32 de = lut[32 + dsym];
-                    const int db = (int)(de >> 16);
-                    if (br.avail < db) { status = SWC_DEFLATE_SYMBOL_NOT_FOUND; goto done; }
-                    const u32 dist = (de & 0xFFFFu) + br.peek(db);
-                    br.skip(db);
-                    if (dist > em.op) { status = SWC_ERR_REFERENCE_TRAP; goto done; }       // :219 negative array index
-                    if ((u64)em.op + length > 0xFFFFFFF0ull) { status = SWC_ERR_UNSUPPORTED; goto done; }
-                    em.match(length, dist);
-                }
-            }
-            if (is_last) break;
+    BlockCtx bc;
+    i64 total_bits = 0;
+    u64 cap64 = 0;
+    u32 pend_len = 0;
+    br.avail = 0;
+    em.op = 0; em.nrec = 0; em.dirty = false; em.acc = 0; em.last_end = 0; em.cap = 0;
+    if (live) {
+        const u64 in_len = a.in_len[unit];
+        cap64 = a.out_cap[unit];
+        em.out = a.out_base + a.out_off[unit];
+        em.rec = a.rec_base + rec_start(a.out_off[unit]);
+        em.cap = cap64 > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (u32)cap64;
+        if (in_len >= (1ull << 32)) {
+            status = SWC_ERR_UNSUPPORTED;
+        } else {
+            br.init(a.in_base, a.in_off[unit], in_len, a.start_bits ? a.start_bits[unit] : 0);
+            total_bits = br.avail;
+            if (br.avail < 10) status = SWC_DEFLATE_WRONG_BLOCK_TYPE;                    // Deflate.swift:36
+            else state = ST_HEADER;
         }
-    done:
-        em.finish();
-        a.consumed_bits[unit] = (u64)(total_bits - br.avail);
     }
-    if (status == SWC_OK && (u64)em.op > cap64) status = SWC_ERR_OUTPUT_OVERFLOW;
-    a.out_len[unit] = em.op;
-    a.status[unit] = status;
-    a.rec_count[unit] = em.nrec;
+    while (__any_sync(SWC_FULL, state != ST_DONE)) {
+#pragma unroll 1
+        for (int k = 0; k < KLIT; k++) {
+            if (state == ST_SYMBOLS) {
+                const int r = litlen_step(br, em, S, bc, lut, state, pend_len);
+                if (r) { status = r; state = ST_DONE; }
+            }
+        }
+        if (state == ST_MATCH) {
+            const int r = dist_step(br, em, S, bc, lut, pend_len);
+            if (r) { status = r; state = ST_DONE; }
+            else state = ST_SYMBOLS;
+        } else if (state == ST_HEADER) {
+            int next = ST_DONE;
+            const int r = begin_block(br, em, S, bc, next);
+            if (r) { status = r; state = ST_DONE; }
+            else state = next;
+        }
+    }
+    if (live) {
+        em.finish();
+        if (status == SWC_OK && (u64)em.op > cap64) status = SWC_ERR_OUTPUT_OVERFLOW;
+        a.consumed_bits[unit] = (u64)(total_bits - br.avail);
+        a.out_len[unit] = em.op;
+        a.status[unit] = status;
+        a.rec_count[unit] = em.nrec;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ K2
@@ -473,11 +526,16 @@ int launch(const BatchArgs &a, cudaStream_t stream) {
     }
     const u64 per_cta = WARPS_PER_CTA * 32;
     const u64 g1 = (a.n + per_cta - 1) / per_cta;
+    timing_mark(stream);
     inflate_huffman_kernel<<<(unsigned)g1, WARPS_PER_CTA * 32, SMEM_BYTES, stream>>>(a);
     count_launch();
+    timing_mark(stream);
+    launch_slow(a, stream);          // no-op unless K1 flagged a unit (over-subscribed Huffman set)
+    timing_mark(stream);
     const u64 g2 = (a.n * 32 + 255) / 256;
     lz_resolve_kernel<<<(unsigned)g2, 256, 0, stream>>>(a);
     count_launch();
+    timing_mark(stream);
     SWC_CUDA_TRY(cudaGetLastError());
     return SWC_OK;
 }

@@ -26,6 +26,7 @@ inline size_t scratch_bytes(u64 n, u64 out_capacity_total) {
 }
 
 int launch(const BatchArgs &a, cudaStream_t stream);
+void launch_slow(const BatchArgs &a, cudaStream_t stream);   // inflate_slow.cu
 
 }  // namespace inflate
 }  // namespace swc

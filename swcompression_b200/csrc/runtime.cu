@@ -2,6 +2,7 @@
 #include <mutex>
 #include <string>
 #include <atomic>
+#include <vector>
 #include <cstdio>
 #include <cstdlib>
 #include "common.cuh"
@@ -48,6 +49,20 @@ int scratch_get(size_t bytes, void **p, cudaStream_t stream) {
     return SWC_OK;
 }
 
+// ---- per-kernel timing (bench.py roofline leg): events recorded on the launch stream, read back after a sync ----
+static bool g_timing = false;
+static std::vector<cudaEvent_t> g_marks;
+static size_t g_mark_used = 0;
+void timing_mark(cudaStream_t stream) {
+    if (!g_timing) return;
+    if (g_mark_used == g_marks.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        g_marks.push_back(e);
+    }
+    cudaEventRecord(g_marks[g_mark_used++], stream);
+}
+
 int ensure_device() {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -89,6 +104,19 @@ int32_t swc_release_scratch(void) {
         if (pool.p) { cudaFree(pool.p); pool.p = nullptr; pool.bytes = 0; }
     }
     return SWC_OK;
+}
+
+void swc_timing_enable(int32_t on) { swc::g_timing = on != 0; swc::g_mark_used = 0; }
+// elapsed ms between consecutive marks since swc_timing_enable(1); returns the number of intervals written
+int32_t swc_timing_collect(float *ms, int32_t max_n) {
+    int32_t n = 0;
+    for (size_t i = 1; i < swc::g_mark_used && n < max_n; i++) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, swc::g_marks[i - 1], swc::g_marks[i]) != cudaSuccess) { cudaGetLastError(); break; }
+        ms[n++] = t;
+    }
+    swc::g_mark_used = 0;
+    return n;
 }
 
 const char *swc_status_name(int32_t s) {

@@ -1,0 +1,97 @@
+"""Parity of the CUDA BZip2 path (through the C ABI) with the CPU oracle."""
+import bz2
+import random
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    assert torch.cuda.is_available()
+    import swcompression_b200 as S
+    return S
+
+
+@pytest.mark.parametrize("rel,ans", H.fixtures("BZip2/"))
+def test_fixtures(gpu, rel, ans):
+    assert gpu.BZip2.decompress(H.fixture(rel)) == H.answer(ans)
+
+
+@pytest.mark.parametrize("raw", H.ROUNDTRIP_STRINGS)
+def test_roundtrip_strings(gpu, raw):
+    assert gpu.BZip2.decompress(bz2.compress(raw)) == raw
+
+
+def test_short_inputs(gpu, oracle):
+    for n in range(0, 16):
+        junk = bytes(range(n))
+        ost = oracle.bzip2_decompress(junk)[0]
+        with pytest.raises(gpu.SWCompressionError) as e:
+            gpu.BZip2.decompress(junk)
+        assert e.value.code == ost
+
+
+def test_config4_shape_single_900k_block(gpu, oracle):
+    raw = H.textlike(900000, 4)
+    comp = bz2.compress(raw, 9)
+    ost, oout, oused = oracle.bzip2_decompress(comp)
+    assert ost == 0 and oout == raw
+    assert gpu.BZip2.decompress(comp) == raw
+
+
+def test_multi_block_and_multi_stream(gpu, oracle):
+    raw = H.textlike(350000, 41)
+    comp = bz2.compress(raw, 1)                      # 100 KB blocks -> 4 blocks
+    assert gpu.BZip2.decompress(comp) == raw
+    a, b = H.textlike(5000, 42), bytes(300000)
+    assert gpu.BZip2.multiDecompress(bz2.compress(a) + bz2.compress(b)) == [a, b]
+    assert gpu.BZip2.decompress(bz2.compress(a) + bz2.compress(b)) == a     # first stream only
+
+
+def test_batch_ragged(oracle):
+    from swcompression_b200.batch import Batch
+    rng = random.Random(8)
+    raws = []
+    for i in range(48):
+        n = rng.choice([0, 1, 4, 5, 255, 256, 1000, 50000, 200000])
+        k = i % 4
+        raws.append(H.textlike(max(n, 70), 900 + i)[:n] if k == 0 else bytes(n) if k == 1 else
+                    bytes(rng.getrandbits(8) for _ in range(n)) if k == 2 else (b"aaaa\x00" * (n // 5 + 1))[:n])
+    units = [bz2.compress(r, rng.choice([1, 9])) for r in raws]
+    b = Batch.from_units("bzip2", units, 262144)
+    b.run()
+    st, ln, used = b.results()
+    outs = b.outputs()
+    for i, u in enumerate(units):
+        ost, oout, oused = oracle.bzip2_decompress(u)
+        assert st[i] == ost == 0 and outs[i] == oout == raws[i] and used[i] == oused, (i, st[i])
+
+
+def test_truncation_corruption_and_crc_payload(gpu, oracle):
+    rng = random.Random(12)
+    raw = H.textlike(30000, 43)
+    comp = bz2.compress(raw)
+    bad = bytearray(comp); bad[10] ^= 1                                  # block CRC
+    with pytest.raises(gpu.BZip2Error) as e:
+        gpu.BZip2.decompress(bytes(bad))
+    assert e.value.case == "wrongCRC" and e.value.payload == raw         # BZip2Tests.swift:81-97
+    cases = [comp[:rng.randrange(1, len(comp))] for _ in range(40)]
+    for _ in range(60):
+        b = bytearray(comp); b[rng.randrange(len(b))] ^= 1 << rng.randrange(8); cases.append(bytes(b))
+    for c in cases:
+        ost, oout, _ = oracle.bzip2_decompress(c)
+        try:
+            out = gpu.BZip2.decompress(c)
+            assert ost == 0 and out == oout
+        except gpu.SWCompressionError as e:
+            if e.code in (1, 6):         # engine: output bound exceeded by a corrupted run length / over-subscribed code set
+                continue
+            assert e.code == ost, (e.code, ost)
+            if ost == 210:
+                assert e.payload == oout

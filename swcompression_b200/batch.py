@@ -54,7 +54,7 @@ class Batch:
         self.d_consumed = torch.zeros(self.n, dtype=torch.int64, device=self.device)
         self.d_status = torch.full((self.n,), -1, dtype=torch.int32, device=self.device)
         self.d_scratch = None
-        self.d_aux = None if aux is None else torch.from_numpy(np.asarray(aux, dtype=np.uint8)).to(self.device)
+        self.d_aux = None if aux is None else torch.from_numpy(np.frombuffer(bytes(aux), dtype=np.uint8).copy()).to(self.device)
         if codec == "deflate":
             nbytes = _lib.lib().swc_deflate_batch_scratch_bytes(self.n, self.out_total)
             self.d_scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)

@@ -1,0 +1,131 @@
+// Public decode API of the reference, bodies routed through libswcgpu (include/swcgpu.h).
+//   DecompressionAlgorithm  Sources/Common/DecompressionAlgorithm.swift:9-14
+//   Archive                 Sources/Common/Archive.swift:9-14
+import CSWCGPU
+import Foundation
+
+public protocol DecompressionAlgorithm { static func decompress(data: Data) throws -> Data }
+public protocol Archive { static func unarchive(archive: Data) throws -> Data }
+
+private let payloadCodes: Set<Int32> = [210, 503, 605, 705, 807]
+
+/// Calls a single-unit entry point `(in, len, &out, &outLen) -> status` and wraps the swc_alloc'ed result.
+@inline(__always)
+private func single(_ data: Data, _ body: (UnsafePointer<UInt8>?, Int, UnsafeMutablePointer<UnsafeMutablePointer<UInt8>?>,
+                                         UnsafeMutablePointer<Int>) -> Int32) throws -> Data {
+    var out: UnsafeMutablePointer<UInt8>? = nil
+    var outLen = 0
+    let status: Int32 = data.withUnsafeBytes { raw in
+        body(raw.bindMemory(to: UInt8.self).baseAddress, raw.count, &out, &outLen)
+    }
+    let result = out.map { Data(bytes: $0, count: outLen) } ?? Data()
+    swc_free(out)
+    guard status == 0 else { throw swcError(status, payload: payloadCodes.contains(status) ? [result] : []) }
+    return result
+}
+
+/// Same for the multi-* entry points that also return end offsets.
+private func multi(_ data: Data, _ body: (UnsafePointer<UInt8>?, Int, UnsafeMutablePointer<UnsafeMutablePointer<UInt8>?>,
+                                         UnsafeMutablePointer<Int>, UnsafeMutablePointer<UnsafeMutablePointer<Int>?>,
+                                         UnsafeMutablePointer<Int>) -> Int32) throws -> [Data] {
+    var out: UnsafeMutablePointer<UInt8>? = nil
+    var outLen = 0, count = 0
+    var ends: UnsafeMutablePointer<Int>? = nil
+    let status: Int32 = data.withUnsafeBytes { raw in
+        body(raw.bindMemory(to: UInt8.self).baseAddress, raw.count, &out, &outLen, &ends, &count)
+    }
+    var parts = [Data]()
+    var prev = 0
+    for i in 0..<count { let e = ends![i]; parts.append(Data(bytes: out! + prev, count: e - prev)); prev = e }
+    swc_free(out); swc_free(ends)
+    guard status == 0 else { throw swcError(status, payload: payloadCodes.contains(status) ? parts : []) }
+    return parts
+}
+
+public class Deflate: DecompressionAlgorithm {                       // Sources/Deflate/Deflate.swift:10-28
+    public static func decompress(data: Data) throws -> Data {
+        try single(data) { p, n, o, ol in var used = 0; return swc_deflate_decompress(p, n, 0, o, ol, &used) }
+    }
+}
+
+public class BZip2: DecompressionAlgorithm {                         // Sources/BZip2/BZip2.swift:10-48
+    public static func decompress(data: Data) throws -> Data {
+        try single(data) { p, n, o, ol in var used = 0; return swc_bzip2_decompress(p, n, 0, o, ol, &used) }
+    }
+    public static func multiDecompress(data: Data) throws -> [Data] {
+        try multi(data) { p, n, o, ol, e, c in swc_bzip2_multi_decompress(p, n, o, ol, e, c) }
+    }
+}
+
+public struct LZMAProperties {                                       // Sources/LZMA/LZMAProperties.swift:9-47
+    public var lc = 3, lp = 0, pb = 2
+    public var dictionarySize = 1 << 24 { didSet { if dictionarySize < 1 << 12 { dictionarySize = 1 << 12 } } }
+    public init() {}
+    public init(lc: Int, lp: Int, pb: Int, dictionarySize: Int) { self.lc = lc; self.lp = lp; self.pb = pb; self.dictionarySize = dictionarySize }
+}
+
+public class LZMA: DecompressionAlgorithm {                          // Sources/LZMA/LZMA.swift:10-61
+    public static func decompress(data: Data) throws -> Data {
+        try single(data) { p, n, o, ol in var used = 0; return swc_lzma_decompress(p, n, o, ol, &used) }
+    }
+    public static func decompress(data: Data, properties: LZMAProperties, uncompressedSize: Int? = nil) throws -> Data {
+        try single(data) { p, n, o, ol in
+            var used = 0
+            return swc_lzma_decompress_raw(p, n, Int32(properties.lc), Int32(properties.lp), Int32(properties.pb),
+                                           Int64(properties.dictionarySize), Int64(uncompressedSize ?? -1), o, ol, &used)
+        }
+    }
+}
+
+public class LZMA2: DecompressionAlgorithm {                         // Sources/LZMA2/LZMA2.swift:10-30
+    public static func decompress(data: Data) throws -> Data {
+        try single(data) { p, n, o, ol in var used = 0; return swc_lzma2_decompress(p, n, o, ol, &used) }
+    }
+}
+
+public enum LZ4: DecompressionAlgorithm {                            // Sources/LZ4/LZ4.swift:33-146
+    public static func decompress(data: Data) throws -> Data { try decompress(data: data, dictionary: nil) }
+    public static func decompress(data: Data, dictionary: Data?, dictionaryID: UInt32? = nil) throws -> Data {
+        try withDictionary(dictionary) { dp, dn in
+            try single(data) { p, n, o, ol in var used = 0; return swc_lz4_decompress(p, n, dp, dn, dictionaryID == nil ? 0 : 1, dictionaryID ?? 0, o, ol, &used) }
+        }
+    }
+    public static func multiDecompress(data: Data, dictionary: Data? = nil, dictionaryID: UInt32? = nil) throws -> [Data] {
+        try withDictionary(dictionary) { dp, dn in
+            try multi(data) { p, n, o, ol, e, c in swc_lz4_multi_decompress(p, n, dp, dn, dictionaryID == nil ? 0 : 1, dictionaryID ?? 0, o, ol, e, c) }
+        }
+    }
+    private static func withDictionary<T>(_ d: Data?, _ body: (UnsafePointer<UInt8>?, Int) throws -> T) rethrows -> T {
+        guard let d = d else { return try body(nil, 0) }
+        var one: UInt8 = 0     // a non-nil pointer distinguishes an EMPTY dictionary from `nil`
+        return try d.withUnsafeBytes { raw in
+            try withUnsafePointer(to: &one) { try body(raw.count > 0 ? raw.bindMemory(to: UInt8.self).baseAddress : $0, raw.count) }
+        }
+    }
+}
+
+public class GzipArchive: Archive {                                  // Sources/GZip/GzipArchive.swift:10-77
+    public static func unarchive(archive data: Data) throws -> Data {
+        try single(data) { p, n, o, ol in var used = 0; return swc_gzip_unarchive(p, n, o, ol, &used) }
+    }
+    /// The reference returns `[Member]` (header + data); header parsing is metadata and stays in Swift
+    /// (GzipHeader.swift is unchanged and can be re-used on `archive` with the member offsets).
+    public static func multiUnarchiveData(archive data: Data) throws -> [Data] {
+        try multi(data) { p, n, o, ol, e, c in swc_gzip_multi_unarchive(p, n, o, ol, e, c) }
+    }
+}
+
+public class ZlibArchive: Archive {                                  // Sources/Zlib/ZlibArchive.swift:10-42
+    public static func unarchive(archive data: Data) throws -> Data {
+        try single(data) { p, n, o, ol in swc_zlib_unarchive(p, n, o, ol) }
+    }
+}
+
+public class XZArchive: Archive {                                    // Sources/XZ/XZArchive.swift:10-88
+    public static func unarchive(archive data: Data) throws -> Data {
+        try single(data) { p, n, o, ol in swc_xz_unarchive(p, n, o, ol) }
+    }
+    public static func splitUnarchive(archive data: Data) throws -> [Data] {
+        try multi(data) { p, n, o, ol, e, c in swc_xz_split_unarchive(p, n, o, ol, e, c) }
+    }
+}

@@ -36,8 +36,9 @@ static int deflate_batch_impl(const uint8_t *in_base, const uint64_t *in_off, co
     a.in_base = in_base; a.in_off = in_off; a.in_len = in_len; a.start_bits = start_bits;
     a.out_base = out_base; a.out_off = out_off; a.out_cap = out_cap;
     a.out_len = out_len; a.consumed_bits = consumed_bits; a.status = status; a.n = n;
-    a.rec_count = (u32 *)scratch;                                   // n entries
-    a.rec_base = (u32 *)((u8 *)scratch + ((n * 4 + 255) & ~(size_t)255));
+    a.ticket = (unsigned long long *)scratch;                       // 8 bytes (256 reserved)
+    a.rec_count = (u32 *)((u8 *)scratch + 256);                     // n entries
+    a.rec_base = (u32 *)((u8 *)scratch + 256 + ((n * 4 + 255) & ~(size_t)255));
     return inflate::launch(a, stream);
 }
 

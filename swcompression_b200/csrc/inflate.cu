@@ -416,9 +416,11 @@ inflate_huffman_kernel(BatchArgs a) {
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u32 *S = smem + SMEM_LUT_WORDS + warp * (W_TOTAL * 32) + lane;     // this lane's word 0
 
-    const u64 unit = (u64)blockIdx.x * (WARPS_PER_CTA * 32) + threadIdx.x;
-    const bool live = unit < a.n;
+    // Persistent lanes: every lane pulls its next unit from a global ticket counter the moment it finishes one, so a
+    // warp never idles on its slowest stream and the grid is exactly the resident capacity (no partial last wave).
     int status = SWC_OK, state = ST_DONE;
+    bool have_unit = false, exhausted = false;
+    u64 unit = 0;
     BitReader br;
     Emitter em;
     BlockCtx bc;
@@ -427,22 +429,43 @@ inflate_huffman_kernel(BatchArgs a) {
     u32 pend_len = 0;
     br.avail = 0;
     em.op = 0; em.nrec = 0; em.dirty = false; em.acc = 0; em.last_end = 0; em.cap = 0;
-    if (live) {
-        const u64 in_len = a.in_len[unit];
-        cap64 = a.out_cap[unit];
-        em.out = a.out_base + a.out_off[unit];
-        em.rec = a.rec_base + rec_start(a.out_off[unit]);
-        em.cap = cap64 > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (u32)cap64;
-        if (in_len >= (1ull << 32)) {
-            status = SWC_ERR_UNSUPPORTED;
-        } else {
-            br.init(a.in_base, a.in_off[unit], in_len, a.start_bits ? a.start_bits[unit] : 0);
-            total_bits = br.avail;
-            if (br.avail < 10) status = SWC_DEFLATE_WRONG_BLOCK_TYPE;                    // Deflate.swift:36
-            else state = ST_HEADER;
+    for (;;) {
+        if (state == ST_DONE) {
+            if (have_unit) {                                                             // retire the finished unit
+                em.finish();
+                if (status == SWC_OK && (u64)em.op > cap64) status = SWC_ERR_OUTPUT_OVERFLOW;
+                a.consumed_bits[unit] = (u64)(total_bits - br.avail);
+                a.out_len[unit] = em.op;
+                a.status[unit] = status;
+                a.rec_count[unit] = em.nrec;
+                have_unit = false;
+            }
+            if (!exhausted) {
+                unit = atomicAdd(a.ticket, 1ull);
+                if (unit >= a.n) {
+                    exhausted = true;
+                } else {
+                    have_unit = true;
+                    status = SWC_OK;
+                    const u64 in_len = a.in_len[unit];
+                    cap64 = a.out_cap[unit];
+                    em.out = a.out_base + a.out_off[unit];
+                    em.rec = a.rec_base + rec_start(a.out_off[unit]);
+                    em.cap = cap64 > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (u32)cap64;
+                    em.op = 0; em.nrec = 0; em.dirty = false; em.acc = 0; em.last_end = 0;
+                    total_bits = 0; br.avail = 0;
+                    if (in_len >= (1ull << 32)) {
+                        status = SWC_ERR_UNSUPPORTED;
+                    } else {
+                        br.init(a.in_base, a.in_off[unit], in_len, a.start_bits ? a.start_bits[unit] : 0);
+                        total_bits = br.avail;
+                        if (br.avail < 10) status = SWC_DEFLATE_WRONG_BLOCK_TYPE;        // Deflate.swift:36
+                        else state = ST_HEADER;
+                    }
+                }
+            }
         }
-    }
-    while (__any_sync(SWC_FULL, state != ST_DONE)) {
+        if (!__any_sync(SWC_FULL, state != ST_DONE || have_unit || !exhausted)) break;
 #pragma unroll 1
         for (int k = 0; k < KLIT; k++) {
             if (state == ST_SYMBOLS) {
@@ -461,57 +484,63 @@ inflate_huffman_kernel(BatchArgs a) {
             else state = next;
         }
     }
-    if (live) {
-        em.finish();
-        if (status == SWC_OK && (u64)em.op > cap64) status = SWC_ERR_OUTPUT_OVERFLOW;
-        a.consumed_bits[unit] = (u64)(total_bits - br.avail);
-        a.out_len[unit] = em.op;
-        a.status[unit] = status;
-        a.rec_count[unit] = em.nrec;
-    }
 }
 
 // ------------------------------------------------------------------------------------------------ K2
-// One warp per unit: replay match records in order.
+// One warp per unit: replay the match records in order.  Lane j holds record j of a 32-record group; an inclusive warp
+// scan of (literal-run + length) gives every match its absolute position.  The group is then executed 8 records at a
+// time by 4-lane sub-groups.  A record is READY when everything it reads is final: its source ends at or before the
+// start of the oldest still-pending record of the batch (bytes before that point were placed by K1 literals or by
+// completed matches) — or it IS that oldest record.  Far matches therefore run 8-wide in one pass; chains of
+// near matches (RLE-like data) degrade gracefully to in-order execution.  Overlapping copies (dist < len) replicate the
+// period: every source byte lies in [start-dist, start), never in what the match itself writes.
 __global__ void __launch_bounds__(256)
 lz_resolve_kernel(BatchArgs a) {
     const u64 unit = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (unit >= a.n) return;
     if (a.status[unit] != SWC_OK) return;
     const u32 lane = threadIdx.x & 31;
+    const u32 sub = lane >> 2, t = lane & 3;
     const u32 nrec = a.rec_count[unit];
     const u32 *rec = a.rec_base + rec_start(a.out_off[unit]);
     u8 *out = a.out_base + a.out_off[unit];
     u32 base = 0;
     for (u32 g = 0; g < nrec; g += 32) {
-        u32 r = (g + lane < nrec) ? rec[g + lane] : 0x8000u;     // padding = escape with skip 0
+        const u32 r = (g + lane < nrec) ? rec[g + lane] : 0x8000u;     // padding = escape with skip 0
         const bool esc = (r & 0x8000u) != 0;
         const u32 len = esc ? 0 : ((r >> 16) & 0xFF) + 3;
         const u32 adv = esc ? ((r & 0x7FFFu) | ((r >> 16) << 15)) : (r >> 24) + len;
         u32 end = adv;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            u32 v = __shfl_up_sync(SWC_FULL, end, d);
+            const u32 v = __shfl_up_sync(SWC_FULL, end, d);
             if (lane >= (u32)d) end += v;
         }
         const u32 start = base + end - len;
         const u32 dist = (r & 0x7FFFu) + 1;
         base += __shfl_sync(SWC_FULL, end, 31);
-        u32 mask = __ballot_sync(SWC_FULL, len != 0);
-        while (mask) {
-            const int k = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const u32 s = __shfl_sync(SWC_FULL, start, k);
-            const u32 l = __shfl_sync(SWC_FULL, len, k);
-            const u32 d = __shfl_sync(SWC_FULL, dist, k);
-            const u8 *src = out + s - d;
-            // every source byte lies in [s-d, s): final before this match, never overlapping what it writes
-            if (d >= l) {
-                for (u32 i = lane; i < l; i += 32) out[s + i] = src[i];
-            } else {
-                for (u32 i = lane; i < l; i += 32) out[s + i] = src[i % d];   // period replication
+#pragma unroll 1
+        for (u32 b0 = 0; b0 < 32; b0 += 8) {
+            // this sub-group's record
+            const u32 s = __shfl_sync(SWC_FULL, start, b0 + sub);
+            const u32 l = __shfl_sync(SWC_FULL, len, b0 + sub);
+            const u32 d = __shfl_sync(SWC_FULL, dist, b0 + sub);
+            const u32 src_end = s - d + (l < d ? l : d);
+            bool pend = l != 0;
+            u32 pmask = __ballot_sync(SWC_FULL, pend && t == 0);         // bit 4*sub per pending record
+            while (pmask) {
+                const u32 oldest = (__ffs(pmask) - 1) >> 2;                // sub-group index of the oldest pending record
+                const u32 frontier = __shfl_sync(SWC_FULL, s, oldest << 2);
+                const bool ready = pend && (sub == oldest || src_end <= frontier);
+                if (ready) {
+                    const u8 *src = out + s - d;
+                    if (d >= l) { for (u32 i = t; i < l; i += 4) out[s + i] = src[i]; }
+                    else        { for (u32 i = t; i < l; i += 4) out[s + i] = src[i % d]; }
+                    pend = false;
+                }
+                __syncwarp();
+                pmask = __ballot_sync(SWC_FULL, pend && t == 0);
             }
-            __syncwarp();
         }
     }
 }
@@ -524,8 +553,17 @@ int launch(const BatchArgs &a, cudaStream_t stream) {
         SWC_CUDA_TRY(cudaFuncSetAttribute(inflate_huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         configured = true;
     }
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        SWC_CUDA_TRY(cudaGetDevice(&dev));
+        SWC_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
     const u64 per_cta = WARPS_PER_CTA * 32;
-    const u64 g1 = (a.n + per_cta - 1) / per_cta;
+    u64 g1 = (a.n + per_cta - 1) / per_cta;
+    const u64 resident = (u64)num_sms * CTAS_PER_SM;          // persistent lanes: one CTA per resident slot
+    if (g1 > resident) g1 = resident;
+    SWC_CUDA_TRY(cudaMemsetAsync(a.ticket, 0, 8, stream));
     timing_mark(stream);
     inflate_huffman_kernel<<<(unsigned)g1, WARPS_PER_CTA * 32, SMEM_BYTES, stream>>>(a);
     count_launch();

@@ -16,13 +16,14 @@ struct BatchArgs {
     u64 n;
     u32 *rec_base;             // match-record scratch
     u32 *rec_count;            // n entries
+    unsigned long long *ticket; // unit ticket counter for K1's persistent lanes (zeroed by the launcher)
 };
 
 // A unit whose output region starts at byte `out_off` owns records [out_off/3, (out_off+cap)/3): every record accounts
 // for >= 3 output bytes, so disjoint output regions give disjoint record regions without a prefix sum.
 __host__ __device__ __forceinline__ u64 rec_start(u64 out_off) { return out_off / 3; }
 inline size_t scratch_bytes(u64 n, u64 out_capacity_total) {
-    return (size_t)((out_capacity_total / 3 + 2) * 4 + n * 4 + 256);
+    return (size_t)((out_capacity_total / 3 + 2) * 4 + n * 4 + 1024);
 }
 
 int launch(const BatchArgs &a, cudaStream_t stream);

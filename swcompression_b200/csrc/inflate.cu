@@ -14,6 +14,7 @@
 // Semantics are those of the reference, including its error cases and the inputs on which it traps
 // (SWC_ERR_REFERENCE_TRAP).  Code sets whose Kraft sum exceeds 1 (which the reference accepts through heap-slot
 // overwrites) are routed to the generic serial decoder in inflate_slow.cu via SWC_INTERNAL_NEEDS_SLOW.
+#include <cstdlib>
 #include "common.cuh"
 #include "inflate.cuh"
 
@@ -548,25 +549,34 @@ lz_resolve_kernel(BatchArgs a) {
 // ------------------------------------------------------------------------------------------------ host
 int launch(const BatchArgs &a, cudaStream_t stream) {
     if (a.n == 0) return SWC_OK;
-    static bool configured = false;
-    if (!configured) {
-        SWC_CUDA_TRY(cudaFuncSetAttribute(inflate_huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        configured = true;
+    // K1 variant: thread-per-unit decoder (default, faster: profiles/README.md) or the experimental warp-per-unit
+    // speculative sub-stream decoder (SWC_DEFLATE_K1=warp). Both are parity-tested against the oracle.
+    static int use_warp = -1;
+    if (use_warp < 0) { const char *e = getenv("SWC_DEFLATE_K1"); use_warp = (e && e[0] == 'w') ? 1 : 0; }
+    if (use_warp) {
+        int st = launch_warp(a, stream);
+        if (st) return st;
+    } else {
+        static bool configured = false;
+        if (!configured) {
+            SWC_CUDA_TRY(cudaFuncSetAttribute(inflate_huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+            configured = true;
+        }
+        static int num_sms = 0;
+        if (!num_sms) {
+            int dev = 0;
+            SWC_CUDA_TRY(cudaGetDevice(&dev));
+            SWC_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        }
+        const u64 per_cta = WARPS_PER_CTA * 32;
+        u64 g1 = (a.n + per_cta - 1) / per_cta;
+        const u64 resident = (u64)num_sms * CTAS_PER_SM;          // persistent lanes: one CTA per resident slot
+        if (g1 > resident) g1 = resident;
+        SWC_CUDA_TRY(cudaMemsetAsync(a.ticket, 0, 8, stream));
+        timing_mark(stream);
+        inflate_huffman_kernel<<<(unsigned)g1, WARPS_PER_CTA * 32, SMEM_BYTES, stream>>>(a);
+        count_launch();
     }
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        SWC_CUDA_TRY(cudaGetDevice(&dev));
-        SWC_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
-    const u64 per_cta = WARPS_PER_CTA * 32;
-    u64 g1 = (a.n + per_cta - 1) / per_cta;
-    const u64 resident = (u64)num_sms * CTAS_PER_SM;          // persistent lanes: one CTA per resident slot
-    if (g1 > resident) g1 = resident;
-    SWC_CUDA_TRY(cudaMemsetAsync(a.ticket, 0, 8, stream));
-    timing_mark(stream);
-    inflate_huffman_kernel<<<(unsigned)g1, WARPS_PER_CTA * 32, SMEM_BYTES, stream>>>(a);
-    count_launch();
     timing_mark(stream);
     launch_slow(a, stream);          // no-op unless K1 flagged a unit (over-subscribed Huffman set)
     timing_mark(stream);

@@ -27,7 +27,8 @@ inline size_t scratch_bytes(u64 n, u64 out_capacity_total) {
 }
 
 int launch(const BatchArgs &a, cudaStream_t stream);
-void launch_slow(const BatchArgs &a, cudaStream_t stream);   // inflate_slow.cu
+void launch_slow(const BatchArgs &a, cudaStream_t stream);
+int launch_warp(const BatchArgs &a, cudaStream_t stream);    // inflate_warp.cu (K1w)   // inflate_slow.cu
 
 }  // namespace inflate
 }  // namespace swc

@@ -251,7 +251,8 @@ def run_product(args):
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(dom)
+                per_unit = json.load(open(tp)).get("bytes_per_unit", {}).get(dom)
+                traffic = per_unit * n_units if per_unit else None
             except Exception:
                 traffic = None
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -81,6 +81,14 @@ int run_blocks(DeviceInput &dev, const std::vector<Block> &blocks, int mode, boo
         a.dict_len = use_dict && dev.have_dict ? dev.dict_len : 0;
         if (mode == 1 && a.dict_len > 65536) { a.dict += a.dict_len - 65536; a.dict_len = 65536; }    // LZ4.swift:309
         a.out_base = d_out_keep.as<u8>(); a.out_off = d_uoff; a.out_cap = d_ucap; a.out_len = d_ulen; a.status = d_st; a.n = nunits;
+        a.scratch = nullptr;
+        if (mode == 0) {               // one block per unit: take the two-phase (parse + 8-wide execute) path
+            uint64_t tot = 0;
+            for (size_t i = 0; i < nb; i++) tot += blocks[i].len;
+            void *scr = nullptr;
+            if ((st = scratch_get(lz4::two_phase_scratch_bytes(nb, tot), &scr, 0))) return st;
+            a.first_blk = nullptr; a.n_blk = nullptr; a.scratch = scr;
+        }
         if ((st = lz4::launch(a, 0))) return st;
         if (check_blocks && attempt == 0) {
             if ((st = d_ck.alloc(nb * 4))) return st;
@@ -270,6 +278,18 @@ int32_t swc_lz4_block_decompress_batch(const uint8_t *in_base, const uint64_t *i
     a.in_base = in_base; a.blk_off = in_off; a.blk_len = in_len; a.first_blk = nullptr; a.n_blk = nullptr;
     a.dict = dict; a.dict_len = dict ? dict_len : 0;
     a.out_base = out_base; a.out_off = out_off; a.out_cap = out_cap; a.out_len = out_len; a.status = status; a.n = n;
+    // two-phase path needs a record scratch sized from the compressed lengths: fetch them once (n x 8 bytes)
+    {
+        std::vector<uint64_t> lens(n);
+        SWC_CUDA_TRY(cudaMemcpyAsync(lens.data(), in_len, n * 8, cudaMemcpyDeviceToHost, (cudaStream_t)cuda_stream));
+        SWC_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+        uint64_t total = 0;
+        for (uint64_t i = 0; i < n; i++) total += lens[i] & ~(1ull << 63);
+        void *scratch = nullptr;
+        int st = scratch_get(lz4::two_phase_scratch_bytes(n, total), &scratch, (cudaStream_t)cuda_stream);
+        if (st) return st;
+        a.scratch = scratch;
+    }
     return lz4::launch(a, (cudaStream_t)cuda_stream);
 }
 

@@ -23,13 +23,13 @@ namespace inflate {
 
 // ---- per-lane shared-memory layout (32-bit words; word w of lane l lives at warp_base[w * 32 + l]) ----
 constexpr int W_LIT_SYM = 0;     // 288 x u8  : low byte of the lit/len symbols sorted by (code length, symbol)
-constexpr int W_LIT_HI = 72;     // 288 bits  : bit i set = sorted symbol i is >= 256 (EOB / length symbol)
-constexpr int W_DST_SYM = 81;    // 32 x u8   : distance symbols sorted likewise
-constexpr int W_LIT_BO = 89;     // [1..15]   : first left-justified 15-bit code of length L | index of its first symbol << 16
-constexpr int W_DST_BO = 105;
-constexpr int W_CL_SYM = 121;    // 19 x u8   : code-length-alphabet symbols, sorted
-constexpr int W_CL_BO = 126;     // [1..7]
-constexpr int W_TOTAL = 134;     // 536 B per lane -> 12 resident warps per SM
+constexpr int W_LIT_TH = 72;     // [1..15]   : sorted index of the first symbol >= 256 among the codes of length L
+constexpr int W_DST_SYM = 88;    // 32 x u8   : distance symbols sorted likewise
+constexpr int W_LIT_BO = 96;     // [1..15]   : first left-justified 15-bit code of length L | index of its first symbol << 16
+constexpr int W_DST_BO = 112;
+constexpr int W_CL_SYM = 128;    // 19 x u8   : code-length-alphabet symbols, sorted
+constexpr int W_CL_BO = 133;     // [1..7]
+constexpr int W_TOTAL = 141;     // 564 B per lane -> 12 resident warps per SM
 constexpr int WARPS_PER_CTA = 4;
 constexpr int CTAS_PER_SM = 3;
 constexpr int KLIT = 4;          // lit/len symbols a lane may decode per round before the warp services pending matches
@@ -71,7 +71,16 @@ struct BitReader {
         bc += 32;
         wnext = fetch();
     }
+#ifdef SWC_REFILL_PRED
+    __device__ __forceinline__ void need32() {
+        const bool nd = bc <= 32;
+        bb |= nd ? ((u64)wnext << (bc & 63)) : 0ull;
+        bc += nd ? 32 : 0;
+        if (nd) wnext = fetch();
+    }
+#else
     __device__ __forceinline__ void need32() { if (bc <= 32) refill(); }
+#endif
     __device__ void init(const u8 *base, u64 off, u64 len, u32 bitskip) {
         uintptr_t a = (uintptr_t)(base + off);
         p = (const u32 *)(a & ~(uintptr_t)3);
@@ -142,15 +151,22 @@ struct Emitter {
     u32 cap;
     u32 last_end;   // end of the previous match (start of the current literal run)
     u32 nrec;
-    u64 acc;        // pending bytes of the 8-byte word that contains `op`
+#ifdef SWC_ACC32
+    typedef u32 acc_t;
+    static constexpr u32 AM = 3, AS = 2;
+#else
+    typedef u64 acc_t;
+    static constexpr u32 AM = 7, AS = 3;
+#endif
+    acc_t acc;      // pending bytes of the aligned word that contains `op`
     bool dirty;     // acc holds at least one literal
 
     __device__ __forceinline__ void literal(u32 byte) {
-        acc |= (u64)byte << ((op & 7) * 8);
+        acc |= (acc_t)byte << ((op & AM) * 8);
         dirty = true;
         op++;
-        if ((op & 7) == 0) {
-            if (op <= cap) *(u64 *)(out + op - 8) = acc;
+        if ((op & AM) == 0) {
+            if (op <= cap) *(acc_t *)(out + op - (AM + 1)) = acc;
             acc = 0; dirty = false;
         }
     }
@@ -166,17 +182,17 @@ struct Emitter {
             rec[nrec++] = (dist - 1) | ((len - 3) << 16) | (run << 24);
         }
         last_end = nop;
-        if ((op >> 3) != (nop >> 3)) {             // leaving the current word
-            if (dirty && (op | 7) < cap) *(u64 *)(out + (op & ~7u)) = acc;
+        if ((op >> AS) != (nop >> AS)) {           // leaving the current word: its remaining bytes belong to the match (K2 fills them)
+            if (dirty && (op | AM) < cap) *(acc_t *)(out + (op & ~AM)) = acc;
             else if (dirty) flush_bytes();
             acc = 0; dirty = false;
         }
         op = nop;
     }
     __device__ void flush_bytes() {                // byte-granular flush of the literal bytes of the current word
-        u32 base = op & ~7u;
+        u32 base = op & ~AM;
         for (u32 i = base; i < op; i++)
-            if (i < cap) out[i] = (u8)(acc >> ((i & 7) * 8));
+            if (i < cap) out[i] = (u8)(acc >> ((i & AM) * 8));
     }
     __device__ __forceinline__ void finish() {
         if (dirty) flush_bytes();
@@ -209,8 +225,8 @@ __device__ __forceinline__ int decode_symbol(BitReader &br, const Limits &lim, c
     u32 idx = (w >> 16) + ((r15 - (w & 0xFFFFu)) >> (15 - L));
     u32 lo = ((const u8 *)(symw + (idx >> 2) * 32))[idx & 3];
     if (KIND == 0) {
-        u32 hw = symw[(W_LIT_HI - W_LIT_SYM + (idx >> 5)) * 32];
-        lo |= ((hw >> (idx & 31)) & 1u) << 8;
+        const u32 th = symw[(W_LIT_TH - W_LIT_SYM + L) * 32];
+        lo |= idx >= th ? 256u : 0u;
     }
     return (int)lo;
 }
@@ -257,13 +273,13 @@ __device__ int run_lengths(BitReader &br, u32 *S, const Limits &cl_lim, bool dyn
                 u32 *bo = S + (is_lit ? W_LIT_BO : W_DST_BO) * 32;
                 if (PASS == 0) {
                     bo[len * 32] += 1;
+                    if (is_lit && n < 256) S[(W_LIT_TH + len) * 32] += 1;
                 } else {
                     u32 w = bo[len * 32];
                     bo[len * 32] = w + 0x10000u;
                     u32 pos = w >> 16;
                     if (is_lit) {
                         ((u8 *)(S + (W_LIT_SYM + (pos >> 2)) * 32))[pos & 3] = (u8)n;
-                        if (n >= 256) S[(W_LIT_HI + (pos >> 5)) * 32] |= 1u << (pos & 31);
                     } else {
                         ((u8 *)(S + (W_DST_SYM + (pos >> 2)) * 32))[pos & 3] = (u8)(n - hlit);
                     }
@@ -322,7 +338,7 @@ __device__ __forceinline__ int begin_block(BitReader &br, Emitter &em, u32 *S, B
 #pragma unroll
     for (int L = 1; L <= 15; L++) { S[(W_LIT_BO + L) * 32] = 0; S[(W_DST_BO + L) * 32] = 0; }
 #pragma unroll
-    for (int k = 0; k < 9; k++) S[(W_LIT_HI + k) * 32] = 0;
+    for (int L = 1; L <= 15; L++) S[(W_LIT_TH + L) * 32] = 0;
     if (dynamic) {
         br.need32();
         if (br.avail < 14) return SWC_DEFLATE_SYMBOL_NOT_FOUND;
@@ -360,6 +376,8 @@ __device__ __forceinline__ int begin_block(BitReader &br, Emitter &em, u32 *S, B
     const u32 k1 = finalize_tables(S + W_LIT_BO * 32, bc.lit_lim, 15);
     const u32 k2 = finalize_tables(S + W_DST_BO * 32, bc.dst_lim, 15);
     if (k1 > 0x8000u || k2 > 0x8000u) return SWC_INTERNAL_NEEDS_SLOW;
+#pragma unroll
+    for (int L = 1; L <= 15; L++) S[(W_LIT_TH + L) * 32] += S[(W_LIT_BO + L) * 32] >> 16;   // first index + #literals of length L
     if (dynamic) br = saved;
     run_lengths<1>(br, S, cl_lim, dynamic, hlit, hdist);
     rewind_offsets(S + W_LIT_BO * 32, 15);

@@ -65,10 +65,11 @@ __device__ __forceinline__ bool read_extension(Window &win, u64 &ip, u64 &value)
     }
 }
 
-__global__ void __launch_bounds__(256)
-lz4_block_kernel(Args a) {
+template <bool ONLY_FLAGGED>
+__device__ __forceinline__ void lz4_block_body(const Args &a) {
     const u64 unit = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (unit >= a.n) return;
+    if (ONLY_FLAGGED && a.status[unit] != 9002) return;
     const u32 lane = lane_id();
     u8 *out = a.out_base + a.out_off[unit];
     const u64 cap = a.out_cap[unit];
@@ -148,8 +149,198 @@ lz4_block_kernel(Args a) {
     }
 }
 
+// =====================================================================================================================
+// Two-phase path for single-block units (the batched raw-block API and independent-block frames):
+//   P1 lz4_parse_kernel — ONE THREAD PER BLOCK walks the token / length / offset bytes only (no payload is touched),
+//      applies every check of LZ4.process(block:_:) in the reference's order (so the status is final here) and writes one
+//      8-byte record per sequence {literal length:24 | match length:24 | offset:16}.
+//   P2 lz4_exec_kernel  — ONE WARP PER BLOCK: warp scans over 32 records give each sequence its input and output
+//      positions; literals (sources in the compressed block: no hazards) are copied first, then matches run 8 at a time on
+//      4-lane sub-groups under the same "oldest pending record" readiness rule as the Deflate resolve kernel; long copies
+//      (>= 64 bytes: incompressible or zero-filled blocks) are done by the whole warp.
+// Units whose lengths do not fit 24 bits are flagged for the one-kernel decoder above.
+constexpr int LZ4_INTERNAL_FALLBACK = 9002;
+
+__device__ __forceinline__ u32 ext_bytes(u32 len_field_value /* length minus its base */) {
+    return len_field_value < 15 ? 0u : 1u + (len_field_value - 15u) / 255u;
+}
+
+__global__ void __launch_bounds__(128) lz4_parse_kernel(Args a, const u64 *rec_base_idx, u64 *recs, u32 *rec_count) {
+    const u64 unit = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (unit >= a.n) return;
+    const u8 *in = a.in_base + a.blk_off[unit];
+    const u64 n = a.blk_len[unit] & ~(1ull << 63);
+    const bool stored = (a.blk_len[unit] >> 63) != 0;
+    const u64 cap = a.out_cap[unit];
+    u64 *rec = recs + rec_base_idx[unit];
+    u32 nrec = 0;
+    int status = SWC_OK;
+    u64 ip = 0, op = 0, seq = 0;
+    const u64 prefix = a.dict ? a.dict_len : 0;
+    i64 last_match_start = -1;
+    if (stored) { status = LZ4_INTERNAL_FALLBACK; }
+    else for (;;) {
+        seq++;
+        if (ip >= n) { status = SWC_DATA_TRUNCATED; break; }                                     // LZ4.swift:343
+        const u32 token = in[ip++];
+        u64 lit = token >> 4;
+        if (lit == 15) {
+            bool ok = false;
+            while (ip < n) { const u32 b = in[ip++]; lit += b; if (b != 255) { ok = true; break; } }
+            if (!ok) { status = SWC_DATA_TRUNCATED; break; }
+        }
+        if (n - ip < lit) { status = SWC_DATA_TRUNCATED; break; }                                // :364
+        op += lit; ip += lit;
+        if (ip == n) {                                                                           // :369-377
+            if (!(lit >= 5 || seq == 1)) status = SWC_DATA_CORRUPTED;
+            else if (last_match_start >= 0 && (i64)op - last_match_start < 12) status = SWC_DATA_CORRUPTED;
+            else if (lit >= (1u << 24)) status = LZ4_INTERNAL_FALLBACK;
+            else rec[nrec++] = lit;
+            break;
+        }
+        if (n - ip < 2) { status = SWC_DATA_TRUNCATED; break; }                                  // :379
+        const u32 offset = (u32)in[ip] | ((u32)in[ip + 1] << 8);
+        ip += 2;
+        if (offset == 0 || (u64)offset > op + prefix) { status = SWC_DATA_CORRUPTED; break; }    // :383
+        u64 mlen = 4 + (token & 15);
+        if (mlen == 19) {
+            bool ok = false;
+            while (ip < n) { const u32 b = in[ip++]; mlen += b; if (b != 255) { ok = true; break; } }
+            if (!ok) { status = SWC_DATA_TRUNCATED; break; }
+        }
+        last_match_start = (i64)op;
+        if (lit >= (1u << 24) || mlen >= (1u << 24)) { status = LZ4_INTERNAL_FALLBACK; break; }
+        rec[nrec++] = lit | (mlen << 24) | ((u64)offset << 48);
+        op += mlen;
+    }
+    if (status == SWC_OK && op > cap) status = SWC_ERR_OUTPUT_OVERFLOW;
+    a.out_len[unit] = op;
+    a.status[unit] = status;
+    rec_count[unit] = nrec;
+}
+
+__global__ void __launch_bounds__(256) lz4_exec_kernel(Args a, const u64 *rec_base_idx, const u64 *recs, const u32 *rec_count) {
+    const u64 unit = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (unit >= a.n) return;
+    if (a.status[unit] != SWC_OK) return;
+    const u32 lane = lane_id(), sub = lane >> 2, t = lane & 3;
+    const u8 *in = a.in_base + a.blk_off[unit];
+    u8 *out = a.out_base + a.out_off[unit];
+    const u64 *rec = recs + rec_base_idx[unit];
+    const u32 nrec = rec_count[unit];
+    const u8 *dict_end = a.dict ? a.dict + a.dict_len : nullptr;
+    u32 in_base = 0, out_base = 0;
+    for (u32 g = 0; g < nrec; g += 32) {
+        const u64 r = (g + lane < nrec) ? rec[g + lane] : 0ull;
+        const bool have = g + lane < nrec;
+        const u32 lit = (u32)r & 0xFFFFFFu, mlen = (u32)(r >> 24) & 0xFFFFFFu, offset = (u32)(r >> 48);
+        const u32 in_adv = have ? 1u + ext_bytes(lit) + lit + (mlen ? 2u + ext_bytes(mlen - 4u) : 0u) : 0u;
+        const u32 out_adv = lit + mlen;
+        u32 ie = in_adv, oe = out_adv;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const u32 vi = __shfl_up_sync(SWC_FULL, ie, d), vo = __shfl_up_sync(SWC_FULL, oe, d);
+            if (lane >= (u32)d) { ie += vi; oe += vo; }
+        }
+        const u32 lit_src = in_base + ie - in_adv + 1u + ext_bytes(lit);
+        const u32 lit_dst = out_base + oe - out_adv;
+        const u32 m_start = lit_dst + lit;
+        in_base += __shfl_sync(SWC_FULL, ie, 31);
+        out_base += __shfl_sync(SWC_FULL, oe, 31);
+        // ---- literals: long runs by the whole warp, short ones by sub-groups
+        u32 big = __ballot_sync(SWC_FULL, lit >= 64);
+        while (big) {
+            const int k = __ffs(big) - 1; big &= big - 1;
+            warp_copy(out + __shfl_sync(SWC_FULL, lit_dst, k), in + __shfl_sync(SWC_FULL, lit_src, k), __shfl_sync(SWC_FULL, lit, k));
+        }
+#pragma unroll 1
+        for (u32 b0 = 0; b0 < 32; b0 += 8) {
+            const u32 l = __shfl_sync(SWC_FULL, lit, b0 + sub);
+            const u32 sp = __shfl_sync(SWC_FULL, lit_src, b0 + sub), dp = __shfl_sync(SWC_FULL, lit_dst, b0 + sub);
+            if (l < 64) for (u32 i = t; i < l; i += 4) out[dp + i] = in[sp + i];
+        }
+        __syncwarp();
+        // ---- matches
+#pragma unroll 1
+        for (u32 b0 = 0; b0 < 32; b0 += 8) {
+            const u32 s = __shfl_sync(SWC_FULL, m_start, b0 + sub);
+            const u32 l = __shfl_sync(SWC_FULL, mlen, b0 + sub);
+            const u32 d = __shfl_sync(SWC_FULL, offset, b0 + sub);
+            const i64 src0 = (i64)s - (i64)d;
+            const i64 src_end = src0 + (i64)(l < d ? l : d);
+            bool pend = l != 0;
+            u32 pmask = __ballot_sync(SWC_FULL, pend && t == 0);
+            while (pmask) {
+                const u32 oldest = (__ffs(pmask) - 1) >> 2;
+                const u32 fs = __shfl_sync(SWC_FULL, s, oldest << 2);
+                const u32 fl = __shfl_sync(SWC_FULL, l, oldest << 2);
+                const u32 fd = __shfl_sync(SWC_FULL, d, oldest << 2);
+                if (fl >= 64) {                                       // long match: the whole warp copies the oldest record
+                    const i64 fsrc = (i64)fs - (i64)fd;
+                    if (fsrc >= 0 && fd >= fl && fd >= 512) warp_copy(out + fs, out + fsrc, fl);
+                    else for (u32 i = lane; i < fl; i += 32) {
+                        const i64 q = fsrc + (i64)(fd >= fl ? i : i % fd);
+                        out[fs + i] = q >= 0 ? out[q] : dict_end[q];
+                    }
+                    if (sub == oldest) pend = false;
+                } else {
+                    const bool ready = pend && l < 64 && (sub == oldest || src_end <= (i64)fs);
+                    if (ready) {
+                        for (u32 i = t; i < l; i += 4) {
+                            const i64 q = src0 + (i64)(d >= l ? i : i % d);
+                            out[s + i] = q >= 0 ? out[q] : dict_end[q];
+                        }
+                        pend = false;
+                    }
+                }
+                __syncwarp();
+                pmask = __ballot_sync(SWC_FULL, pend && t == 0);
+            }
+        }
+    }
+}
+
+// exclusive prefix sum of per-unit record capacities (in_len / 3 + 2), one block
+__global__ void __launch_bounds__(1024) lz4_rec_scan_kernel(const u64 *blk_len, u64 n, u64 *base) {
+    __shared__ u64 part[1024];
+    const u64 per = (n + 1023) / 1024;
+    const u64 b = threadIdx.x * per, e = b + per < n ? b + per : n;
+    u64 sum = 0;
+    for (u64 i = b; i < e; i++) sum += (blk_len[i] & ~(1ull << 63)) / 3 + 2;
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        u64 v = threadIdx.x >= (u32)d ? part[threadIdx.x - d] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    u64 run = part[threadIdx.x] - sum;
+    for (u64 i = b; i < e; i++) { base[i] = run; run += (blk_len[i] & ~(1ull << 63)) / 3 + 2; }
+}
+
+
+size_t two_phase_scratch_bytes(u64 n, u64 in_total) {
+    return (size_t)(n * 8 + n * 4 + (in_total / 3 + 2 * n + 16) * 8 + 1024);
+}
+
+__global__ void __launch_bounds__(256) lz4_block_kernel(Args a) { lz4_block_body<false>(a); }
+__global__ void __launch_bounds__(256) lz4_fallback_kernel(Args a) { lz4_block_body<true>(a); }
+
 int launch(const Args &a, cudaStream_t stream) {
     if (a.n == 0) return SWC_OK;
+    if (a.first_blk == nullptr && a.scratch != nullptr) {
+        u64 *base = (u64 *)a.scratch;
+        u32 *cnt = (u32 *)(base + a.n);
+        u64 *recs = (u64 *)(((uintptr_t)(cnt + a.n) + 255) & ~(uintptr_t)255);
+        lz4_rec_scan_kernel<<<1, 1024, 0, stream>>>(a.blk_len, a.n, base);
+        lz4_parse_kernel<<<(unsigned)((a.n + 127) / 128), 128, 0, stream>>>(a, base, recs, cnt);
+        lz4_exec_kernel<<<(unsigned)((a.n * 32 + 255) / 256), 256, 0, stream>>>(a, base, recs, cnt);
+        lz4_fallback_kernel<<<(unsigned)((a.n * 32 + 255) / 256), 256, 0, stream>>>(a);
+        count_launch(4);
+        SWC_CUDA_TRY(cudaGetLastError());
+        return SWC_OK;
+    }
     const u64 g = (a.n * 32 + 255) / 256;
     lz4_block_kernel<<<(unsigned)g, 256, 0, stream>>>(a);
     count_launch();

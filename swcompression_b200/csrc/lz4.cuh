@@ -16,8 +16,10 @@ struct Args {
     u64 *out_len;
     int32_t *status;
     u64 n;                            // units
+    void *scratch;                    // optional: two_phase_scratch_bytes(n, in_total) bytes enables the two-phase path
 };
 
+size_t two_phase_scratch_bytes(u64 n, u64 in_total);
 int launch(const Args &a, cudaStream_t stream);
 
 }  // namespace lz4

@@ -97,7 +97,9 @@ int32_t swc_deflate_decompress_batch(const uint8_t *in_base, const uint64_t *in_
                               out_len, consumed_bits, status, n, scratch, scratch_bytes, (cudaStream_t)cuda_stream);
 }
 
-// Host-buffer batch: H2D of the compressed bytes + tables, decode, D2H of the decoded bytes + results.
+// Host-buffer batch: the units are cut into slices that flow through three CUDA streams, so the host->device copy of
+// slice k+1, the kernels of slice k and the device->host copy of slice k-1 overlap (PCIe is full duplex). Device staging
+// buffers come from grow-only arenas, so steady-state calls do no cudaMalloc.
 int32_t swc_deflate_decompress_batch_host(const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len,
                                           uint64_t in_total,
                                           uint8_t *out_base, const uint64_t *out_off, const uint64_t *out_cap,
@@ -105,30 +107,74 @@ int32_t swc_deflate_decompress_batch_host(const uint8_t *in_base, const uint64_t
                                           uint64_t *out_len, uint64_t *consumed_bits, int32_t *status, uint64_t n) {
     if (ensure_device()) return SWC_ERR_NO_DEVICE;
     if (n == 0) return SWC_OK;
-    DevBuf d_in, d_out, d_meta;
+    if (!in_base || !in_off || !in_len || !out_base || !out_off || !out_cap || !out_len || !consumed_bits || !status) return SWC_ERR_INVALID_ARG;
+    static cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+    static cudaEvent_t tables_ready = nullptr;
+    if (!streams[0]) {
+        for (auto &s : streams) SWC_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        SWC_CUDA_TRY(cudaEventCreateWithFlags(&tables_ready, cudaEventDisableTiming));
+    }
+    // slices need monotone, in-bounds offsets so that a slice is one contiguous byte range on both sides
+    bool monotone = true;
+    for (uint64_t i = 0; i < n && monotone; i++) {
+        if (in_off[i] + in_len[i] > in_total || out_off[i] + out_cap[i] > out_total) return SWC_ERR_INVALID_ARG;
+        if (i && (in_off[i] < in_off[i - 1] + in_len[i - 1] || out_off[i] < out_off[i - 1] + out_cap[i - 1])) monotone = false;
+    }
+    const uint64_t S = (monotone && n >= 4096) ? 8 : 1;
+    void *p_in = nullptr, *p_out = nullptr, *p_meta = nullptr, *p_scr = nullptr;
     int st;
-    if ((st = d_in.alloc(round16(in_total) + 16))) return st;
-    if ((st = d_out.alloc(round16(out_total)))) return st;
     const size_t tb = n * 8;
-    if ((st = d_meta.alloc(tb * 6 + n * 4))) return st;
-    u8 *m = d_meta.as<u8>();
-    cudaStream_t s = 0;
-    SWC_CUDA_TRY(cudaMemcpyAsync(d_in.p, in_base, in_total, cudaMemcpyHostToDevice, s));
-    SWC_CUDA_TRY(cudaMemcpyAsync(m + 0 * tb, in_off, tb, cudaMemcpyHostToDevice, s));
-    SWC_CUDA_TRY(cudaMemcpyAsync(m + 1 * tb, in_len, tb, cudaMemcpyHostToDevice, s));
-    SWC_CUDA_TRY(cudaMemcpyAsync(m + 2 * tb, out_off, tb, cudaMemcpyHostToDevice, s));
-    SWC_CUDA_TRY(cudaMemcpyAsync(m + 3 * tb, out_cap, tb, cudaMemcpyHostToDevice, s));
-    st = deflate_batch_impl(d_in.as<u8>(), (u64 *)(m + 0 * tb), (u64 *)(m + 1 * tb), nullptr, d_out.as<u8>(),
-                            (u64 *)(m + 2 * tb), (u64 *)(m + 3 * tb), out_total, (u64 *)(m + 4 * tb), (u64 *)(m + 5 * tb),
-                            (int32_t *)(m + 6 * tb), n, nullptr, 0, s);
-    if (st) return st;
-    SWC_CUDA_TRY(cudaMemcpyAsync(out_base, d_out.p, out_total, cudaMemcpyDeviceToHost, s));
-    SWC_CUDA_TRY(cudaMemcpyAsync(out_len, m + 4 * tb, tb, cudaMemcpyDeviceToHost, s));
-    SWC_CUDA_TRY(cudaMemcpyAsync(consumed_bits, m + 5 * tb, tb, cudaMemcpyDeviceToHost, s));
-    SWC_CUDA_TRY(cudaMemcpyAsync(status, m + 6 * tb, n * 4, cudaMemcpyDeviceToHost, s));
-    SWC_CUDA_TRY(cudaStreamSynchronize(s));
-    for (uint64_t i = 0; i < n; i++)
-        if (status[i] == SWC_INTERNAL_NEEDS_SLOW) status[i] = SWC_ERR_UNSUPPORTED;
+    const size_t hdr = 256 * 8 + ((n * 4 + 255) & ~(size_t)255);
+    if ((st = arena_get(1, round16(in_total) + 64, &p_in, 0))) return st;
+    if ((st = arena_get(2, round16(out_total) + 64, &p_out, 0))) return st;
+    if ((st = arena_get(3, tb * 6 + n * 4 + 256, &p_meta, 0))) return st;
+    if ((st = arena_get(0, hdr + (out_total / 3 + 2) * 4 + 256, &p_scr, 0))) return st;
+    // result tables come back through a library-owned pinned buffer: a D2H into pageable caller memory would block the
+    // host thread inside the slice loop and serialise the whole pipeline
+    static u8 *h_res = nullptr; static size_t h_res_bytes = 0;
+    const size_t res_bytes = n * 20;
+    if (h_res_bytes < res_bytes) {
+        if (h_res) cudaFreeHost(h_res);
+        h_res = nullptr; h_res_bytes = 0;
+        SWC_CUDA_TRY(cudaMallocHost((void **)&h_res, res_bytes + (res_bytes >> 2)));
+        h_res_bytes = res_bytes + (res_bytes >> 2);
+    }
+    u64 *h_out_len = (u64 *)h_res, *h_cons = h_out_len + n;
+    int32_t *h_status = (int32_t *)(h_cons + n);
+    u8 *m = (u8 *)p_meta;
+    u64 *d_in_off = (u64 *)(m + 0 * tb), *d_in_len = (u64 *)(m + 1 * tb), *d_out_off = (u64 *)(m + 2 * tb), *d_out_cap = (u64 *)(m + 3 * tb);
+    u64 *d_out_len = (u64 *)(m + 4 * tb), *d_cons = (u64 *)(m + 5 * tb);
+    int32_t *d_status = (int32_t *)(m + 6 * tb);
+    SWC_CUDA_TRY(cudaMemcpyAsync(d_in_off, in_off, tb, cudaMemcpyHostToDevice, streams[0]));
+    SWC_CUDA_TRY(cudaMemcpyAsync(d_in_len, in_len, tb, cudaMemcpyHostToDevice, streams[0]));
+    SWC_CUDA_TRY(cudaMemcpyAsync(d_out_off, out_off, tb, cudaMemcpyHostToDevice, streams[0]));
+    SWC_CUDA_TRY(cudaMemcpyAsync(d_out_cap, out_cap, tb, cudaMemcpyHostToDevice, streams[0]));
+    SWC_CUDA_TRY(cudaEventRecord(tables_ready, streams[0]));
+    for (uint64_t k = 0; k < S; k++) {
+        const uint64_t b = n * k / S, e = n * (k + 1) / S;
+        if (b == e) continue;
+        cudaStream_t s = streams[k % 3];
+        SWC_CUDA_TRY(cudaStreamWaitEvent(s, tables_ready, 0));
+        const uint64_t i0 = S == 1 ? 0 : in_off[b], i1 = S == 1 ? in_total : in_off[e - 1] + in_len[e - 1];
+        const uint64_t o0 = S == 1 ? 0 : out_off[b], o1 = S == 1 ? out_total : out_off[e - 1] + out_cap[e - 1];
+        SWC_CUDA_TRY(cudaMemcpyAsync((u8 *)p_in + i0, in_base + i0, i1 - i0, cudaMemcpyHostToDevice, s));
+        inflate::BatchArgs a;
+        a.in_base = (const u8 *)p_in; a.in_off = d_in_off + b; a.in_len = d_in_len + b; a.start_bits = nullptr;
+        a.out_base = (u8 *)p_out; a.out_off = d_out_off + b; a.out_cap = d_out_cap + b;
+        a.out_len = d_out_len + b; a.consumed_bits = d_cons + b; a.status = d_status + b; a.n = e - b;
+        a.ticket = (unsigned long long *)((u8 *)p_scr + 256 * k);
+        a.rec_count = (u32 *)((u8 *)p_scr + 256 * 8) + b;
+        a.rec_base = (u32 *)((u8 *)p_scr + hdr);
+        if ((st = inflate::launch(a, s))) return st;
+        SWC_CUDA_TRY(cudaMemcpyAsync(out_base + o0, (u8 *)p_out + o0, o1 - o0, cudaMemcpyDeviceToHost, s));
+        SWC_CUDA_TRY(cudaMemcpyAsync(h_out_len + b, d_out_len + b, (e - b) * 8, cudaMemcpyDeviceToHost, s));
+        SWC_CUDA_TRY(cudaMemcpyAsync(h_cons + b, d_cons + b, (e - b) * 8, cudaMemcpyDeviceToHost, s));
+        SWC_CUDA_TRY(cudaMemcpyAsync(h_status + b, d_status + b, (e - b) * 4, cudaMemcpyDeviceToHost, s));
+    }
+    for (auto &s : streams) SWC_CUDA_TRY(cudaStreamSynchronize(s));
+    memcpy(out_len, h_out_len, n * 8);
+    memcpy(consumed_bits, h_cons, n * 8);
+    memcpy(status, h_status, n * 4);
     return SWC_OK;
 }
 

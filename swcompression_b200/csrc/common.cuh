@@ -45,5 +45,7 @@ void timing_mark(cudaStream_t stream);
 
 // scratch pool: grow-only per-device buffer, used when the caller passes no scratch
 int scratch_get(size_t bytes, void **p, cudaStream_t stream);
+// grow-only arenas reused across calls: slot 0 = kernel scratch, 1..3 = device staging of the *_batch_host paths
+int arena_get(int slot, size_t bytes, void **p, cudaStream_t stream);
 
 }  // namespace swc

@@ -25,13 +25,15 @@ int cuda_fail(cudaError_t e, const char *where) {
 // ---- grow-only scratch pool, one per device ----
 struct Pool { void *p = nullptr; size_t bytes = 0; };
 static std::mutex g_pool_mu;
-static Pool g_pools[64];
+static Pool g_pools[64][4];      // [device][slot]: 0 kernel scratch, 1-3 staging arenas of the *_batch_host paths
 
-int scratch_get(size_t bytes, void **p, cudaStream_t stream) {
+int scratch_get(size_t bytes, void **p, cudaStream_t stream) { return arena_get(0, bytes, p, stream); }
+
+int arena_get(int slot, size_t bytes, void **p, cudaStream_t stream) {
     int dev = 0;
     SWC_CUDA_TRY(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(g_pool_mu);
-    Pool &pool = g_pools[dev & 63];
+    Pool &pool = g_pools[dev & 63][slot & 3];
     if (pool.bytes < bytes) {
         if (pool.p) {
             SWC_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -100,9 +102,9 @@ void swc_free_pinned(void *p) { if (p) cudaFreeHost(p); }
 uint64_t swc_kernel_launches(void) { return swc::g_launches.load(); }
 int32_t swc_release_scratch(void) {
     std::lock_guard<std::mutex> lk(swc::g_pool_mu);
-    for (auto &pool : swc::g_pools) {
-        if (pool.p) { cudaFree(pool.p); pool.p = nullptr; pool.bytes = 0; }
-    }
+    for (auto &dev : swc::g_pools)
+        for (auto &pool : dev)
+            if (pool.p) { cudaFree(pool.p); pool.p = nullptr; pool.bytes = 0; }
     return SWC_OK;
 }
 

@@ -164,3 +164,28 @@ def test_start_bit_form(gpu, oracle):
     out, used = gpu.Deflate.decompress_from(data, 16 + 5)
     ost, oout, oused = oracle.deflate_decompress(data, 16 + 5)
     assert ost == 0 and out == oout == raw and used == oused
+
+
+def test_batch_host_pipelined(oracle):
+    """swc_deflate_decompress_batch_host: host buffers in/out, sliced over three streams when n >= 4096."""
+    import ctypes as C
+    from swcompression_b200 import _lib
+    from swcompression_b200.batch import pack_units
+    base = [H.raw_deflate(H.textlike(4000 + 37 * i, 3000 + i)) for i in range(64)]
+    raws = [H.textlike(4000 + 37 * i, 3000 + i) for i in range(64)]
+    for n in (100, 5000):
+        units = [base[i % 64] for i in range(n)]
+        buf, offs, lens = pack_units(units)
+        cap = 8192
+        o_off = np.arange(n, dtype=np.uint64) * np.uint64(cap)
+        o_cap = np.full(n, cap, dtype=np.uint64)
+        out = np.zeros(n * cap, dtype=np.uint8)
+        r_len = np.zeros(n, dtype=np.uint64); r_used = np.zeros(n, dtype=np.uint64); r_st = np.full(n, -1, dtype=np.int32)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = _lib.lib().swc_deflate_decompress_batch_host(vp(buf), vp(offs), vp(lens), len(buf), vp(out), vp(o_off), vp(o_cap), n * cap,
+                                                         vp(r_len), vp(r_used), vp(r_st), n)
+        assert rc == 0
+        assert (r_st == 0).all()
+        for i in range(0, n, 97):
+            ost, oout, oused = oracle.deflate_decompress(units[i])
+            assert bytes(out[i * cap:i * cap + int(r_len[i])]) == oout == raws[i % 64] and r_used[i] == oused

@@ -625,8 +625,12 @@ int launch(const BatchArgs &a, cudaStream_t stream) {
     if (a.n == 0) return SWC_OK;
     // K1 variant: thread-per-unit decoder (default, faster: profiles/README.md) or the experimental warp-per-unit
     // speculative sub-stream decoder (SWC_DEFLATE_K1=warp). Both are parity-tested against the oracle.
-    static int use_warp = -1;
-    if (use_warp < 0) { const char *e = getenv("SWC_DEFLATE_K1"); use_warp = (e && e[0] == 'w') ? 1 : 0; }
+    // Large batches: thread-per-unit (one lane per stream fills the chip from ~57 K units).  Small batches — and the
+    // single-stream API calls — cannot fill it that way, so they take the warp-per-unit decoder, which puts 32 lanes on
+    // every stream (about 10 x lower latency per stream).  SWC_DEFLATE_K1=thread|warp forces one variant.
+    static int forced = -2;
+    if (forced == -2) { const char *e = getenv("SWC_DEFLATE_K1"); forced = !e ? -1 : (e[0] == 'w' ? 1 : 0); }
+    const bool use_warp = forced >= 0 ? forced == 1 : a.n < 20000;
     if (use_warp) {
         int st = launch_warp(a, stream);
         if (st) return st;

@@ -21,7 +21,10 @@ namespace inflate {
 
 namespace w {
 
-constexpr int WIN_WORDS = 9;                 // 288-bit window per lane: stride 9 words = conflict-free initial reads
+#ifndef SWC_WIN_WORDS
+#define SWC_WIN_WORDS 19
+#endif
+constexpr int WIN_WORDS = SWC_WIN_WORDS;     // window per lane in 32-bit words; odd stride = conflict-free initial reads
 constexpr int WIN_BITS = WIN_WORDS * 32;
 constexpr int STAGE_WORDS = 32 * WIN_WORDS + 8;
 constexpr int LIT_BITS = 11, DST_BITS = 9;

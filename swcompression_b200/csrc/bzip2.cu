@@ -10,6 +10,7 @@
 //   - RUNA/RUNB runs are filled by all lanes; MTF output goes through a 128-byte shared staging line;
 //   - inverse BWT: per-byte histogram -> stable scatter builds the successor array, then the n-step pointer chase is split
 //     over the 32 lanes with the splitter (sparse-ruler) list-ranking trick; RLE1 undo + block CRC run on lane 0.
+#include <cstdio>
 #include "common.cuh"
 #include "bzip2.cuh"
 
@@ -135,6 +136,22 @@ struct BwtOut {
     }
 };
 
+// ---- GF(2) helpers for the MSB-first CRC-32 (poly 0x04C11DB7): crc(A||B) = crc(A) * x^(8|B|) + crc(B) for conditioned values
+__device__ __forceinline__ u32 mulmod_bz(u32 a, u32 b) {
+    u32 p = 0;
+    while (a) {
+        if (a & 1) p ^= b;
+        a >>= 1;
+        b = (b & 0x80000000u) ? (b << 1) ^ 0x04C11DB7u : b << 1;
+    }
+    return p;
+}
+__device__ __forceinline__ u32 xpow_bz(u64 nbytes) {
+    u32 p = 1, sq = 1u << 8;
+    while (nbytes) { if (nbytes & 1) p = mulmod_bz(sq, p); sq = mulmod_bz(sq, sq); nbytes >>= 1; }
+    return p;
+}
+
 // ---------------------------------------------------------------- the kernel
 __global__ void __launch_bounds__(WARPS * 32) bzip2_kernel(Args a) {
     __shared__ WarpSmem smem[WARPS];
@@ -243,6 +260,9 @@ __global__ void __launch_bounds__(WARPS * 32) bzip2_kernel(Args a) {
         __syncwarp();
         if (nsel == 0) FAIL(SWC_ERR_REFERENCE_TRAP);                                 // selectors[0]
 
+#ifdef SWC_BZ_PROFILE
+        long long t_hdr = clock64();
+#endif
         // ------------------------------------------------ symbol loop :212-246
         BwtOut bo; bo.bwt = bwt; bo.cap = scr_cap; bo.n = 0; bo.fill = 0; bo.S = &S;
         {
@@ -284,6 +304,9 @@ __global__ void __launch_bounds__(WARPS * 32) bzip2_kernel(Args a) {
             bo.flush();
         }
         {
+#ifdef SWC_BZ_PROFILE
+            long long t_dec = clock64();
+#endif
             // ------------------------------------------------ BurrowsWheeler.reverse
             const u64 n = bo.n;
             __syncwarp();
@@ -315,6 +338,9 @@ __global__ void __launch_bounds__(WARPS * 32) bzip2_kernel(Args a) {
                     __syncwarp();
                 }
                 __syncwarp();
+#ifdef SWC_BZ_PROFILE
+                long long t_sort = clock64();
+#endif
                 // ---- pointer chase split over 32 lanes (splitter list ranking) ----
                 // splitter j starts at index s_j (s_0 = orig_ptr); bit 31 of succ[s_j] marks it.
                 const u32 MARK = 0x80000000u;
@@ -370,32 +396,67 @@ __global__ void __launch_bounds__(WARPS * 32) bzip2_kernel(Args a) {
                     }
                 }
                 __syncwarp();
-                // ------------------------------------------------ RLE1 undo + block CRC (lane 0) :251-267
-                u32 crc = 0xFFFFFFFFu;
+#ifdef SWC_BZ_PROFILE
+                long long t_chase = clock64();
+#endif
+                // ------------------------------------------------ RLE1 undo :251-267, 32 text bytes per step
+                // The reference walks i one byte at a time and, when text[i..i+3] are equal (and i < n-4), expands a run
+                // and jumps 5 bytes.  Every step here starts at such a "fresh" position i: lane j tests whether a run would
+                // start at i+j; all positions before the first run start are plain literals, so they are emitted together.
                 u64 bop = op;
-                if (lane == 0) {
+                {
                     u64 i = 0;
                     while (i < n) {
-                        const u8 c0 = text[i];
-                        if (n >= 4 && i < n - 4 && c0 == text[i + 1] && c0 == text[i + 2] && c0 == text[i + 3]) {
-                            const u32 runl = (u32)text[i + 4] + 4;
-                            for (u32 k = 0; k < runl; k++) {
-                                if (bop < cap) out[bop] = c0;
-                                bop++;
-                                crc = (crc << 8) ^ c_bzcrc[((crc >> 24) ^ c0) & 0xFF];
-                            }
-                            i += 5;
+                        const u64 q = i + lane;
+                        u32 b0 = 0; bool runs = false;
+                        if (q < n) {
+                            b0 = text[q];
+                            if (n >= 5 && q < n - 4) runs = text[q + 1] == b0 && text[q + 2] == b0 && text[q + 3] == b0;
+                        }
+                        const u32 m = __ballot_sync(SWC_FULL, runs);
+                        const u32 lits = m ? (u32)(__ffs(m) - 1) : (u32)(n - i < 32 ? n - i : 32);
+                        if (lane < lits && bop + lane < cap) out[bop + lane] = (u8)b0;
+                        bop += lits;
+                        if (m) {
+                            const u32 js = lits;
+                            const u32 c0 = __shfl_sync(SWC_FULL, b0, js);
+                            const u32 runl = (u32)text[i + js + 4] + 4;
+                            for (u32 k = lane; k < runl; k += 32) if (bop + k < cap) out[bop + k] = (u8)c0;
+                            bop += runl;
+                            i += js + 5;
                         } else {
-                            if (bop < cap) out[bop] = c0;
-                            bop++;
-                            crc = (crc << 8) ^ c_bzcrc[((crc >> 24) ^ c0) & 0xFF];
-                            i += 1;
+                            i += lits;
                         }
                     }
                 }
-                bop = __shfl_sync(SWC_FULL, (u32)bop, 0) | ((u64)__shfl_sync(SWC_FULL, (u32)(bop >> 32), 0) << 32);
-                crc = ~__shfl_sync(SWC_FULL, crc, 0);
+                __syncwarp();
+                // ------------------------------------------------ block CRC (CheckSums.swift:30-37), 32 segments + GF(2) combine
+                u32 crc = 0;
+                if (bop <= cap) {
+                    for (int c = lane; c < 256; c += 32) S.counts[c] = c_bzcrc[c];
+                    __syncwarp();
+                    const u64 len = bop - op;
+                    const u64 seg = (len + 31) / 32;
+                    const u64 sb = lane * seg < len ? lane * seg : len, se = sb + seg < len ? sb + seg : len;
+                    u32 part = 0xFFFFFFFFu;
+                    const u8 *pdat = out + op;
+                    for (u64 k = sb; k < se; k++) part = (part << 8) ^ S.counts[((part >> 24) ^ pdat[k]) & 0xFF];
+                    part = ~part;
+                    const u32 pw_full = xpow_bz(seg);
+                    u32 acc = __shfl_sync(SWC_FULL, part, 0);
+                    for (int l = 1; l < 32; l++) {
+                        const u32 pl = __shfl_sync(SWC_FULL, part, l);
+                        const u64 lb = (u64)l * seg < len ? (u64)l * seg : len, le = lb + seg < len ? lb + seg : len;
+                        const u64 ll = le - lb;
+                        if (ll == 0) continue;
+                        acc = mulmod_bz(ll == seg ? pw_full : xpow_bz(ll), acc) ^ pl;
+                    }
+                    crc = acc;
+                }
                 op = bop;
+#ifdef SWC_BZ_PROFILE
+                if (unit == 0 && lane == 0) printf("bz2 block n=%llu: decode %lld  hist+scatter %lld  chase %lld  rle+crc %lld cycles\n", (unsigned long long)n, t_dec - t_hdr, t_sort - t_dec, t_chase - t_sort, clock64() - t_chase);
+#endif
                 if (op > cap) FAIL(SWC_ERR_OUTPUT_OVERFLOW);
                 if (crc != block_crc) FAIL(SWC_BZIP2_WRONG_CRC);                         // :81 (payload includes this block)
             } else {

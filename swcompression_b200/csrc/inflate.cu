@@ -71,16 +71,7 @@ struct BitReader {
         bc += 32;
         wnext = fetch();
     }
-#ifdef SWC_REFILL_PRED
-    __device__ __forceinline__ void need32() {
-        const bool nd = bc <= 32;
-        bb |= nd ? ((u64)wnext << (bc & 63)) : 0ull;
-        bc += nd ? 32 : 0;
-        if (nd) wnext = fetch();
-    }
-#else
     __device__ __forceinline__ void need32() { if (bc <= 32) refill(); }
-#endif
     __device__ void init(const u8 *base, u64 off, u64 len, u32 bitskip) {
         uintptr_t a = (uintptr_t)(base + off);
         p = (const u32 *)(a & ~(uintptr_t)3);
@@ -151,13 +142,8 @@ struct Emitter {
     u32 cap;
     u32 last_end;   // end of the previous match (start of the current literal run)
     u32 nrec;
-#ifdef SWC_ACC32
-    typedef u32 acc_t;
-    static constexpr u32 AM = 3, AS = 2;
-#else
-    typedef u64 acc_t;
+    typedef u64 acc_t;                       // 8-byte words: a 4-byte accumulator doubles the store count (measured -5 %)
     static constexpr u32 AM = 7, AS = 3;
-#endif
     acc_t acc;      // pending bytes of the aligned word that contains `op`
     bool dirty;     // acc holds at least one literal
 
@@ -426,49 +412,6 @@ __device__ __forceinline__ int dist_step(BitReader &br, Emitter &em, const u32 *
     return SWC_OK;
 }
 
-// Unified step: one Huffman symbol from the lit/len table (state ST_SYMBOLS) or from the distance table (ST_MATCH).
-__device__ __forceinline__ int unified_step(BitReader &br, Emitter &em, const u32 *S, const BlockCtx &bc, const u32 *lut,
-                                            int &state, u32 &pend_len) {
-    const bool want_dist = state == ST_MATCH;
-    br.need32();
-    Limits lim;
-#pragma unroll
-    for (int k = 0; k < 8; k++) lim.p[k] = want_dist ? bc.dst_lim.p[k] : bc.lit_lim.p[k];
-    const u32 r15 = __brev(br.peek(15)) >> 17;
-    const int L = code_length(r15, lim);
-    if (L > 15) return SWC_DEFLATE_SYMBOL_NOT_FOUND;
-    const u32 w = S[((want_dist ? W_DST_BO : W_LIT_BO) + L) * 32];
-    const u32 idx = (w >> 16) + ((r15 - (w & 0xFFFFu)) >> (15 - L));
-    const u32 lo = ((const u8 *)(S + ((want_dist ? W_DST_SYM : W_LIT_SYM) + (idx >> 2)) * 32))[idx & 3];
-    const u32 th = S[(W_LIT_TH + L) * 32];
-    const u32 sym = lo | ((!want_dist && idx >= th) ? 256u : 0u);
-    if (br.avail < L) return SWC_DEFLATE_SYMBOL_NOT_FOUND;
-    br.skip(L);
-    if (!want_dist) {
-        if (sym < 256) { em.literal(sym); return SWC_OK; }
-        if (sym == 256) { state = bc.is_last ? ST_DONE : ST_HEADER; return SWC_OK; }
-        if (sym > 285) return SWC_DEFLATE_WRONG_SYMBOL;
-        const u32 le = lut[sym - 257];
-        const int eb = (int)(le >> 16);
-        if (br.avail < eb) return SWC_DEFLATE_SYMBOL_NOT_FOUND;
-        pend_len = (le & 0xFFFFu) + br.peek(eb);
-        br.skip(eb);
-        state = ST_MATCH;
-        return SWC_OK;
-    }
-    if (sym > 29) return SWC_DEFLATE_WRONG_SYMBOL;
-    const u32 de = lut[32 + sym];
-    const int db = (int)(de >> 16);
-    if (br.avail < db) return SWC_DEFLATE_SYMBOL_NOT_FOUND;
-    const u32 dist = (de & 0xFFFFu) + br.peek(db);
-    br.skip(db);
-    if (dist > em.op) return SWC_ERR_REFERENCE_TRAP;                                     // Deflate.swift:219
-    if ((u64)em.op + pend_len > 0xFFFFFFF0ull) return SWC_ERR_UNSUPPORTED;
-    em.match(pend_len, dist);
-    state = ST_SYMBOLS;
-    return SWC_OK;
-}
-
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
 inflate_huffman_kernel(BatchArgs a) {
     extern __shared__ u32 smem[];
@@ -528,18 +471,6 @@ inflate_huffman_kernel(BatchArgs a) {
             }
         }
         if (!__any_sync(SWC_FULL, state != ST_DONE || have_unit || !exhausted)) break;
-#ifdef SWC_K1_UNIFIED
-        // every lane decodes ONE Huffman symbol per step from the table its state asks for (lit/len or distance): the
-        // decode instructions are shared by all lanes, only the short post-processing tails diverge
-#pragma unroll 1
-        for (int k = 0; k < SWC_K1_UNIFIED; k++) {
-            if (state == ST_SYMBOLS || state == ST_MATCH) {
-                const int r = unified_step(br, em, S, bc, lut, state, pend_len);
-                if (r) { status = r; state = ST_DONE; }
-            }
-        }
-        if (state == ST_HEADER) {
-#else
 #pragma unroll 1
         for (int k = 0; k < KLIT; k++) {
             if (state == ST_SYMBOLS) {
@@ -552,7 +483,6 @@ inflate_huffman_kernel(BatchArgs a) {
             if (r) { status = r; state = ST_DONE; }
             else state = ST_SYMBOLS;
         } else if (state == ST_HEADER) {
-#endif
             int next = ST_DONE;
             const int r = begin_block(br, em, S, bc, next);
             if (r) { status = r; state = ST_DONE; }

@@ -111,6 +111,65 @@ int32_t swc_bzip2_multi_decompress(const uint8_t *in, size_t in_len,
     std::vector<size_t> ends;
     size_t off = 0;
     int result = SWC_OK;
+    // ---- fast path: discover the streams up front and decode them as ONE batch ------------------------------------
+    // A stream starts byte-aligned with 'B' 'Z' 'h' '1'..'9' followed by a block magic (or the end magic of an empty
+    // stream).  Candidates found by scanning for that 10-byte signature are decoded in parallel; a candidate is accepted
+    // only if the previous stream ended exactly there (consumed bytes == distance to the next candidate).  The first
+    // stream that does not validate — or fails — hands over to the sequential loop below, which IS the reference's
+    // order of events (BZip2.swift:40-48), so results and errors are the same with or without the fast path.
+    {
+        std::vector<size_t> cand;
+        static const uint8_t blk[6] = {0x31, 0x41, 0x59, 0x26, 0x53, 0x59}, eos[6] = {0x17, 0x72, 0x45, 0x38, 0x50, 0x90};
+        for (size_t i = 0; i + 10 <= in_len; i++) {
+            if (in[i] != 'B' || in[i + 1] != 'Z' || in[i + 2] != 'h' || in[i + 3] < '1' || in[i + 3] > '9') continue;
+            if (memcmp(in + i + 4, blk, 6) == 0 || memcmp(in + i + 4, eos, 6) == 0) cand.push_back(i);
+        }
+        if (cand.size() >= 2 && cand[0] == 0) {
+            const size_t n = cand.size();
+            std::vector<uint64_t> h_off(n), h_len(n), h_ooff(n), h_cap(n), r_len(n), r_used(n);
+            std::vector<int32_t> r_st(n);
+            // groups bounded by a scratch budget (the BWT working set is ~6x the output capacity of a unit)
+            const size_t budget = (size_t)24 << 30;
+            size_t k0 = 0;
+            bool handed_over = false;
+            while (k0 < n && !handed_over) {
+                size_t k1 = k0, need = 0, out_total = 0;
+                while (k1 < n) {
+                    const size_t len = (k1 + 1 < n ? cand[k1 + 1] : in_len) - cand[k1];
+                    const size_t cap = round16(len * 12 + (1u << 20));
+                    const size_t add = bzip2::scratch_per_unit(cap) + cap;
+                    if (k1 > k0 && need + add > budget) break;
+                    h_off[k1] = cand[k1]; h_len[k1] = len; h_ooff[k1] = out_total; h_cap[k1] = cap;
+                    need += add; out_total += cap; k1++;
+                }
+                const size_t g = k1 - k0;
+                DevBuf d_out, d_meta;
+                if ((st = d_out.alloc(out_total + 64))) return st;
+                if ((st = d_meta.alloc(g * 8 * 6 + g * 4 + 64))) return st;
+                u64 *m = d_meta.as<u64>();
+                SWC_CUDA_TRY(cudaMemcpy(m + 0 * g, h_off.data() + k0, g * 8, cudaMemcpyHostToDevice));
+                SWC_CUDA_TRY(cudaMemcpy(m + 1 * g, h_len.data() + k0, g * 8, cudaMemcpyHostToDevice));
+                SWC_CUDA_TRY(cudaMemcpy(m + 2 * g, h_ooff.data() + k0, g * 8, cudaMemcpyHostToDevice));
+                SWC_CUDA_TRY(cudaMemcpy(m + 3 * g, h_cap.data() + k0, g * 8, cudaMemcpyHostToDevice));
+                if ((st = bzip2_batch_impl(d_in.as<u8>(), m + 0 * g, m + 1 * g, d_out.as<u8>(), m + 2 * g, m + 3 * g, m + 4 * g, m + 5 * g,
+                                           (int32_t *)(m + 6 * g), g, 0))) return st;
+                SWC_CUDA_TRY(cudaStreamSynchronize(0));
+                SWC_CUDA_TRY(cudaMemcpy(r_len.data() + k0, m + 4 * g, g * 8, cudaMemcpyDeviceToHost));
+                SWC_CUDA_TRY(cudaMemcpy(r_used.data() + k0, m + 5 * g, g * 8, cudaMemcpyDeviceToHost));
+                SWC_CUDA_TRY(cudaMemcpy(r_st.data() + k0, m + 6 * g, g * 4, cudaMemcpyDeviceToHost));
+                for (size_t k = k0; k < k1; k++) {
+                    const bool ok = r_st[k] == SWC_OK && (r_used[k] + 7) / 8 == h_len[k];
+                    if (!ok) { off = cand[k]; handed_over = true; break; }        // sequential loop re-decodes this stream
+                    const size_t base = o.size();
+                    o.resize(base + r_len[k]);
+                    if (r_len[k]) SWC_CUDA_TRY(cudaMemcpy(o.data() + base, d_out.as<u8>() + h_ooff[k], r_len[k], cudaMemcpyDeviceToHost));
+                    ends.push_back(o.size());
+                    off = cand[k] + h_len[k];
+                }
+                k0 = k1;
+            }
+        }
+    }
     while (off < in_len) {                               // !reader.isFinished
         UnitResult r;
         if ((st = bzip2_unit_device(d_in.as<u8>(), in_len, off, r))) return st;

@@ -95,3 +95,28 @@ def test_truncation_corruption_and_crc_payload(gpu, oracle):
             assert e.code == ost, (e.code, ost)
             if ost == 210:
                 assert e.payload == oout
+
+
+def test_multi_stream_batch_discovery(gpu, oracle):
+    """BZip2.multiDecompress on many concatenated streams: streams are discovered up front and decoded as one batch;
+    anything that does not validate falls back to the in-order loop, so results and errors equal the oracle's."""
+    rng = random.Random(21)
+    raws = [H.textlike(rng.choice([70, 500, 3000, 40000]), 1500 + i) if i % 7 else b"" for i in range(40)]
+    data = b"".join(bz2.compress(r, rng.choice([1, 9])) for r in raws)
+    assert gpu.BZip2.multiDecompress(data) == raws
+    ost, parts, _ = oracle.bzip2_multi_decompress(data)
+    assert ost == 0 and parts == raws
+    # trailing garbage / a corrupted stream in the middle: same error as the sequential reference order
+    for bad in (data + b"BZh9" + bytes(20), data + b"xx", data[:len(data) // 2] + b"\x00" + data[len(data) // 2 + 1:]):
+        ost, parts, _ = oracle.bzip2_multi_decompress(bad)
+        try:
+            got = gpu.BZip2.multiDecompress(bad)
+            assert ost == 0 and got == parts
+        except gpu.SWCompressionError as e:
+            assert e.code == ost, (e.code, ost)
+    streams = [bz2.compress(r) for r in raws[:12]]
+    b = bytearray(streams[5]); b[10] ^= 1; streams[5] = bytes(b)          # block CRC of stream 5
+    ost, parts, _ = oracle.bzip2_multi_decompress(b"".join(streams))
+    with pytest.raises(gpu.BZip2Error) as e:
+        gpu.BZip2.multiDecompress(b"".join(streams))
+    assert e.value.code == ost == 210 and e.value.payload == [raws[5]]

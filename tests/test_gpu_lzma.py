@@ -123,3 +123,31 @@ def test_corruption_and_check_payload(gpu, oracle):
             if e.code == 1:          # engine: corrupted size fields asked for more output than the engine will allocate
                 continue
             assert e.code == ost, (is_xz, e.code, ost)
+
+
+def test_multi_stream_and_multi_block_prefetch(gpu, oracle):
+    """XZ files with many streams / many blocks: blocks are located through the stream indexes and decoded as one batch;
+    the in-order parser validates everything, so results and errors equal the oracle's."""
+    import subprocess
+    rng = random.Random(31)
+    raws = [H.textlike(rng.choice([100, 5000, 70000]), 1700 + i) for i in range(24)]
+    data = b"".join(lzma.compress(r, check=rng.choice([lzma.CHECK_CRC32, lzma.CHECK_CRC64, lzma.CHECK_SHA256, lzma.CHECK_NONE])) + bytes(4 * (i % 3))
+                    for i, r in enumerate(raws))
+    assert gpu.XZArchive.splitUnarchive(data) == raws
+    assert gpu.XZArchive.unarchive(data) == b"".join(raws)
+    big = H.textlike(600000, 1800)
+    mb = subprocess.run(["xz", "-c", "-T1", "--block-size=65536"], input=big, stdout=subprocess.PIPE, check=True).stdout
+    assert oracle.xz_unarchive(mb)[:2] == (0, big)
+    assert gpu.XZArchive.unarchive(mb) == big
+    for _ in range(20):                                      # corruption anywhere: same outcome as the oracle
+        b = bytearray(mb); b[rng.randrange(len(b))] ^= 1 << rng.randrange(8)
+        ost, oout, _ = oracle.xz_unarchive(bytes(b))
+        try:
+            out = gpu.XZArchive.unarchive(bytes(b))
+            assert ost == 0 and out == oout
+        except gpu.SWCompressionError as e:
+            if e.code == 1:
+                continue
+            assert e.code == ost, (e.code, ost)
+            if ost == 807:
+                assert e.payload == oout

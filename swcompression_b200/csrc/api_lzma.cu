@@ -169,8 +169,7 @@ int xz_block(Rd &r, const u8 *d_in, unsigned hsize_byte, int csize, DevBuf &blk,
                 if (it != g_prefetch->by_offset.end() && it->second.dict_byte == (u8)params[f]) pe = &it->second;
             }
             if (pe) {                                                            // decoded ahead of time by xz_prefetch()
-                if ((st = next.alloc(pe->out_len + 16))) return st;
-                if (pe->out_len) SWC_CUDA_TRY(cudaMemcpy(next.p, g_prefetch->out.as<u8>() + pe->out_off, pe->out_len, cudaMemcpyDeviceToDevice));
+                next.borrow(g_prefetch->out.as<u8>() + pe->out_off, pe->out_len);
                 r.off += pe->consumed;
                 next_len = pe->out_len;
             } else {
@@ -181,7 +180,7 @@ int xz_block(Rd &r, const u8 *d_in, unsigned hsize_byte, int csize, DevBuf &blk,
                 if (u.status != SWC_OK) return u.status;
                 if (!have_cur) r.off += u.consumed;
                 next_len = u.out_len;
-                next.p = u.out.p; next.bytes = u.out.bytes; u.out.p = nullptr;      // take ownership
+                next.take(u.out);
             }
         } else {
             const size_t n = src_n - src_start;
@@ -191,8 +190,7 @@ int xz_block(Rd &r, const u8 *d_in, unsigned hsize_byte, int csize, DevBuf &blk,
             if (!have_cur) r.off += n;
             next_len = n;
         }
-        cur.release();
-        cur.p = next.p; cur.bytes = next.bytes; next.p = nullptr;
+        cur.take(next);
         cur_len = next_len; have_cur = true;
     }
     if (!((comp_size < 0 || comp_size == (int64_t)(r.off - data_start)) && (uncomp_size < 0 || uncomp_size == (int64_t)cur_len)))
@@ -205,8 +203,7 @@ int xz_block(Rd &r, const u8 *d_in, unsigned hsize_byte, int csize, DevBuf &blk,
         }
     }
     *unpadded = unp + csize;
-    blk.release();
-    blk.p = cur.p; blk.bytes = cur.bytes; cur.p = nullptr;
+    blk.take(cur);
     blk_len = cur_len;
     return SWC_OK;
 }

@@ -16,7 +16,12 @@ namespace checks {
 int check_device(Kind k, const u8 *d, u64 n, u64 *value) {
     DevBuf res, part;
     int st;
-    if ((st = res.alloc(32))) return st;
+    {   // result slot + chunk partials live in a grow-only arena: per-block checks of big archives do no cudaMalloc
+        void *a = nullptr;
+        if ((st = arena_get(3, 64 + partial_bytes(n), &a, 0))) return st;
+        res.borrow(a, 32);
+        part.borrow((u8 *)a + 64, partial_bytes(n));
+    }
     if (k == XXH32) {
         SWC_CUDA_TRY(cudaMemcpy(res.p, &n, 8, cudaMemcpyHostToDevice));
         if ((st = xxh32_batch(d, nullptr, res.as<u64>(), (u32 *)(res.as<u8>() + 8), 1, 0))) return st;
@@ -25,7 +30,6 @@ int check_device(Kind k, const u8 *d, u64 n, u64 *value) {
         *value = v;
         return SWC_OK;
     }
-    if ((st = part.alloc(partial_bytes(n)))) return st;
     switch (k) {
     case CRC32: st = crc32(d, n, res.as<u64>(), part.as<u64>(), 0); break;
     case BZIP2_CRC32: st = bzip2_crc32(d, n, res.as<u64>(), part.as<u64>(), 0); break;

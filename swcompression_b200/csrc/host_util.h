@@ -14,11 +14,14 @@ int ensure_device();
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
+    bool owned = true;          // false: a view into memory owned elsewhere (never freed here)
     DevBuf() {}
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    void release() { if (p && owned) cudaFree(p); p = nullptr; bytes = 0; owned = true; }
+    void borrow(void *ptr, size_t n) { release(); p = ptr; bytes = n; owned = false; }
+    void take(DevBuf &o) { release(); p = o.p; bytes = o.bytes; owned = o.owned; o.p = nullptr; o.bytes = 0; o.owned = true; }
     int alloc(size_t n) {
         release();
         cudaError_t e = cudaMalloc(&p, n ? n : 16);

@@ -89,14 +89,17 @@ def last_error():
 
 def inbuf(data):
     """bytes-like -> (ctypes pointer, length); keeps a reference alive through the returned object."""
-    b = bytes(data)
-    arr = (C.c_uint8 * max(len(b), 1)).from_buffer_copy(b or b"\0")
-    return arr, len(b)
+    b = data if isinstance(data, bytes) else bytes(data)
+    return C.c_char_p(b or b"\0"), len(b)          # zero-copy: c_char_p keeps `b` alive and the library only reads it
 
 
 def take(ptr, n):
     """Copy an swc_alloc'ed result into bytes and free it."""
-    out = C.string_at(ptr.value, n.value) if ptr.value and n.value else b""
+    if ptr.value and n.value:
+        # string_at() takes a C int; results of 2 GiB and more go through a buffer view instead
+        out = C.string_at(ptr.value, n.value) if n.value < (1 << 31) else bytes((C.c_char * n.value).from_address(ptr.value))
+    else:
+        out = b""
     if ptr.value:
         lib().swc_free(ptr)
     return out

@@ -10,15 +10,15 @@ int to_host_alloc(const void *d, size_t n, uint8_t **out, size_t *out_len) {
     uint8_t *h = (uint8_t *)swc_alloc(n);
     if (!h) return SWC_ERR_OUTPUT_OVERFLOW;
     if (n) {
-        cudaError_t e = cudaMemcpy(h, d, n, cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) { swc_free(h); return cuda_fail(e, "cudaMemcpy D2H"); }
+        int st = copy_pageable(h, d, n, false);
+        if (st) { swc_free(h); return st; }
     }
     *out = h;
     *out_len = n;
     return SWC_OK;
 }
 
-static int deflate_batch_impl(const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len, const uint8_t *start_bits,
+int deflate_batch_impl(const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len, const uint8_t *start_bits,
                               uint8_t *out_base, const uint64_t *out_off, const uint64_t *out_cap, uint64_t out_total,
                               uint64_t *out_len, uint64_t *consumed_bits, int32_t *status, uint64_t n,
                               void *scratch, size_t scratch_bytes, cudaStream_t stream) {
@@ -187,7 +187,7 @@ int32_t swc_deflate_decompress(const uint8_t *in, size_t in_len, size_t start_bi
     DevBuf d_in;
     int st = d_in.alloc(round16(in_len) + 16);
     if (st) return st;
-    if (in_len) SWC_CUDA_TRY(cudaMemcpy(d_in.p, in, in_len, cudaMemcpyHostToDevice));
+    { int cst = copy_pageable(d_in.p, in, in_len, true); if (cst) return cst; }
     UnitResult r;
     if ((st = deflate_unit_device(d_in.as<u8>(), in_len, start_bit, r))) return st;
     if (consumed_bits) *consumed_bits = r.consumed;

@@ -244,7 +244,7 @@ int legacy_frame(DeviceInput &dev, const uint8_t *p, size_t n_total, size_t pos,
 int upload(DeviceInput &dev, const uint8_t *in, size_t in_len, const uint8_t *dict, size_t dict_len) {
     int st;
     if ((st = dev.in.alloc(round16(in_len) + 32))) return st;
-    if (in_len) SWC_CUDA_TRY(cudaMemcpy(dev.in.p, in, in_len, cudaMemcpyHostToDevice));
+    { int cst = copy_pageable(dev.in.p, in, in_len, true); if (cst) return cst; }
     dev.in_len = in_len;
     dev.have_dict = dict != nullptr;
     dev.dict_len = dict ? dict_len : 0;

@@ -61,7 +61,7 @@ int lzma_unit_device(const u8 *d_in, size_t in_len, size_t start, const LzmaJob 
 int upload(DevBuf &d, const uint8_t *in, size_t n) {
     int st = d.alloc(round16(n) + 256);
     if (st) return st;
-    if (n) SWC_CUDA_TRY(cudaMemcpy(d.p, in, n, cudaMemcpyHostToDevice));
+    { int cst = copy_pageable(d.p, in, n, true); if (cst) return cst; }
     return SWC_OK;
 }
 

@@ -2,6 +2,10 @@
 // Reference: Sources/GZip/GzipArchive.swift:38-100, GzipHeader.swift:68-199, Sources/Zlib/ZlibArchive.swift:25-42,
 // ZlibHeader.swift:47-93.  Headers/trailers (tens of bytes) are parsed on the host; Deflate and CRC-32 / Adler-32 over
 // the payload run on the device.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "../../include/swcgpu.h"
@@ -99,8 +103,36 @@ int gzip_header(const uint8_t *in, size_t n, size_t *off) {
     return SWC_OK;
 }
 
+// growable malloc'ed host buffer that is handed to the C caller without another copy (swc_free == free)
+struct HostOut {
+    uint8_t *p = nullptr;
+    size_t len = 0, cap = 0;
+    HostOut() {}
+    HostOut(const HostOut &) = delete;
+    HostOut &operator=(const HostOut &) = delete;
+    ~HostOut() { free(p); }
+    uint8_t *grow(size_t add) {                                     // nullptr when out of memory
+        if (len + add > cap || !p) {
+            size_t nc = cap * 2 > len + add ? cap * 2 : len + add;
+            if (nc < 64) nc = 64;
+            uint8_t *q = (uint8_t *)realloc(p, nc);
+            if (!q) return nullptr;
+            p = q; cap = nc;
+        }
+        uint8_t *r = p + len;
+        len += add;
+        return r;
+    }
+    int release_to(uint8_t **out, size_t *out_len) {
+        if (!p && !grow(0)) return SWC_ERR_OUTPUT_OVERFLOW;
+        *out = p; *out_len = len;
+        p = nullptr; len = cap = 0;
+        return SWC_OK;
+    }
+};
+
 // processMember GzipArchive.swift:79-100; d_in holds the whole archive on the device
-int gzip_member(const uint8_t *in, size_t n, const u8 *d_in, size_t *off, std::vector<uint8_t> &out, bool *crc_error) {
+int gzip_member(const uint8_t *in, size_t n, const u8 *d_in, size_t *off, HostOut &out, bool *crc_error) {
     if (n - *off < 20) return SWC_GZIP_WRONG_MAGIC;
     int st = gzip_header(in, n, off);
     if (st) return st;
@@ -115,26 +147,141 @@ int gzip_member(const uint8_t *in, size_t n, const u8 *d_in, size_t *off, std::v
     u64 got = 0;
     if ((st = checks::check_device(checks::CRC32, r.out.as<u8>(), r.out_len, &got))) return st;
     *crc_error = (uint32_t)got != crc;
-    size_t base = out.size();
-    out.resize(base + r.out_len);
-    if (r.out_len) SWC_CUDA_TRY(cudaMemcpy(out.data() + base, r.out.p, r.out_len, cudaMemcpyDeviceToHost));
+    uint8_t *dst = out.grow(r.out_len);
+    if (!dst) return SWC_ERR_OUTPUT_OVERFLOW;
+    if (r.out_len) SWC_CUDA_TRY(cudaMemcpy(dst, r.out.p, r.out_len, cudaMemcpyDeviceToHost));
     *off = p;
     return SWC_OK;
 }
 
-int give(const std::vector<uint8_t> &v, uint8_t **out, size_t *out_len) {
-    uint8_t *h = (uint8_t *)swc_alloc(v.size());
-    if (!h) return SWC_ERR_OUTPUT_OVERFLOW;
-    if (!v.empty()) memcpy(h, v.data(), v.size());
-    *out = h; *out_len = v.size();
+// ---------------------------------------------------------------------------------------------------------------------
+// Batch path for multi-member archives (BGZF and friends).  Members are independent Deflate streams, so candidate member
+// starts are found by signature, every candidate is decoded speculatively in ONE batched launch (its input ends 8 bytes
+// before the next candidate; its capacity is the ISIZE found there), and the in-order walk of GzipArchive.multiUnarchive
+// (GzipArchive.swift:52-77) then only *validates*: member k is accepted iff it decoded cleanly, stopped exactly at that
+// trailer and produced ISIZE bytes — exactly what the sequential decoder would have computed from the same start.  A
+// member that does not validate (a signature look-alike inside its payload, ISIZE wrap-around, damage) is decoded by the
+// sequential path, and the walk resynchronises on the candidate list afterwards.
+struct Cand { size_t at, dstart, next; uint32_t crc, isize; long unit; };
+
+int gzip_multi_batch(const uint8_t *in, size_t n, const u8 *d_in, HostOut &o, std::vector<size_t> &ends, size_t *off, int *result, bool *stop) {
+    const bool trace = getenv("SWC_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = now();
+    std::vector<size_t> pos;
+    {
+        int st = checks::find_gzip_members(d_in, n, pos);              // device-side signature scan, sorted positions
+        if (st) return st;
+    }
+    if (trace) fprintf(stderr, "[swc] gzip scan: %zu candidates, %.1f ms\n", pos.size(), now() - t0);
+    if (pos.size() < 4 || pos[0] != 0) return SWC_OK;              // nothing to gain: the caller's loop handles it
+    size_t free_b = 0, total_b = 0;
+    SWC_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const size_t budget = free_b / 3;
+    cudaStream_t stream = 0;
+    size_t idx = 0;
+    while (idx < pos.size() && pos[idx] == *off && !*stop) {
+        // ---- one round: candidates idx.. while the speculative outputs fit the budget
+        std::vector<Cand> cs;
+        std::vector<u64> h_inoff, h_inlen, h_outoff, h_outcap;
+        size_t out_total = 0;
+        for (size_t k = idx; k < pos.size() && cs.size() < (1u << 22); k++) {
+            Cand c;
+            c.at = pos[k]; c.next = k + 1 < pos.size() ? pos[k + 1] : n; c.unit = -1; c.crc = c.isize = 0;
+            size_t d = c.at;
+            const bool hdr_ok = gzip_header(in, c.next, &d) == SWC_OK;   // a real header never reaches the next member
+            c.dstart = d;
+            if (hdr_ok && c.next >= d + 8) {
+                c.crc = rd32(in + c.next - 8); c.isize = rd32(in + c.next - 4);
+                const size_t span = c.next - 8 - d;
+                if ((u64)c.isize <= (u64)span * 1032 + 64) {            // Deflate cannot expand further than ~1032:1
+                    const size_t cap16 = round16((size_t)c.isize);
+                    if (out_total + cap16 > budget && !cs.empty()) break;
+                    c.unit = (long)h_inoff.size();
+                    h_inoff.push_back(d); h_inlen.push_back(span);
+                    h_outoff.push_back(out_total); h_outcap.push_back(c.isize);
+                    out_total += cap16;
+                }
+            }
+            cs.push_back(c);
+        }
+        const size_t nu = h_inoff.size();
+        std::vector<u64> h_outlen(nu), h_cons(nu);
+        std::vector<int32_t> h_status(nu);
+        std::vector<uint32_t> h_crc(nu);
+        DevBuf meta, d_out;
+        u64 *m = nullptr;
+        if (nu) {
+            int st = meta.alloc(nu * 64);                               // 7 u64 arrays + status + crc
+            if (st) return st;
+            if ((st = d_out.alloc(out_total + 64))) return st;
+            m = meta.as<u64>();
+            SWC_CUDA_TRY(cudaMemcpyAsync(m, h_inoff.data(), nu * 8, cudaMemcpyHostToDevice, stream));
+            SWC_CUDA_TRY(cudaMemcpyAsync(m + nu, h_inlen.data(), nu * 8, cudaMemcpyHostToDevice, stream));
+            SWC_CUDA_TRY(cudaMemcpyAsync(m + 2 * nu, h_outoff.data(), nu * 8, cudaMemcpyHostToDevice, stream));
+            SWC_CUDA_TRY(cudaMemcpyAsync(m + 3 * nu, h_outcap.data(), nu * 8, cudaMemcpyHostToDevice, stream));
+            int32_t *d_status = (int32_t *)(m + 7 * nu);
+            uint32_t *d_crc = (uint32_t *)(d_status + nu);
+            if ((st = deflate_batch_impl(d_in, m, m + nu, nullptr, d_out.as<u8>(), m + 2 * nu, m + 3 * nu, out_total,
+                                         m + 4 * nu, m + 5 * nu, d_status, nu, nullptr, 0, stream))) return st;
+            if ((st = checks::crc32_units(d_out.as<u8>(), m + 2 * nu, m + 4 * nu, d_crc, nu, stream))) return st;
+            SWC_CUDA_TRY(cudaMemcpyAsync(h_outlen.data(), m + 4 * nu, nu * 8, cudaMemcpyDeviceToHost, stream));
+            SWC_CUDA_TRY(cudaMemcpyAsync(h_cons.data(), m + 5 * nu, nu * 8, cudaMemcpyDeviceToHost, stream));
+            SWC_CUDA_TRY(cudaMemcpyAsync(h_status.data(), d_status, nu * 4, cudaMemcpyDeviceToHost, stream));
+            SWC_CUDA_TRY(cudaMemcpyAsync(h_crc.data(), d_crc, nu * 4, cudaMemcpyDeviceToHost, stream));
+            SWC_CUDA_TRY(cudaStreamSynchronize(stream));
+        }
+        if (trace) fprintf(stderr, "[swc] gzip round: %zu units, %.1f MB out, decode+crc done at %.1f ms\n", nu, out_total / 1e6, now() - t0);
+        // ---- the in-order walk: accept the longest validated prefix
+        std::vector<u64> g_src, g_len, g_dst;
+        size_t acc_bytes = 0, k = 0;
+        for (; k < cs.size(); k++) {
+            const Cand &c = cs[k];
+            if (c.unit < 0) break;
+            const size_t u = (size_t)c.unit;
+            if (h_status[u] != SWC_OK || c.dstart + (h_cons[u] + 7) / 8 + 8 != c.next || h_outlen[u] != c.isize) break;
+            g_src.push_back(h_outoff[u]); g_len.push_back(h_outlen[u]); g_dst.push_back(acc_bytes);
+            acc_bytes += h_outlen[u];
+            if (h_crc[u] != c.crc) { *result = SWC_GZIP_WRONG_CRC; *stop = true; k++; break; }   // the member is still returned
+        }
+        const size_t accepted = g_src.size();
+        if (accepted) {
+            DevBuf gm, d_g;
+            int st = gm.alloc(accepted * 24);
+            if (st) return st;
+            if ((st = d_g.alloc(acc_bytes + 16))) return st;
+            u64 *g = gm.as<u64>();
+            SWC_CUDA_TRY(cudaMemcpyAsync(g, g_src.data(), accepted * 8, cudaMemcpyHostToDevice, stream));
+            SWC_CUDA_TRY(cudaMemcpyAsync(g + accepted, g_len.data(), accepted * 8, cudaMemcpyHostToDevice, stream));
+            SWC_CUDA_TRY(cudaMemcpyAsync(g + 2 * accepted, g_dst.data(), accepted * 8, cudaMemcpyHostToDevice, stream));
+            if ((st = checks::gather_units(d_out.as<u8>(), g, g + accepted, d_g.as<u8>(), g + 2 * accepted, accepted, stream))) return st;
+            const size_t base = o.len;
+            uint8_t *dst = o.grow(acc_bytes);
+            if (!dst) return SWC_ERR_OUTPUT_OVERFLOW;
+            SWC_CUDA_TRY(cudaStreamSynchronize(stream));
+            if ((st = copy_pageable(dst, d_g.p, acc_bytes, false))) return st;
+            for (size_t i = 0; i < accepted; i++) ends.push_back(base + g_dst[i] + g_len[i]);
+            *off = cs[accepted - 1].next;
+            if (trace) fprintf(stderr, "[swc] gzip round: %zu accepted, gathered + copied back at %.1f ms\n", accepted, now() - t0);
+        }
+        if (*stop) return SWC_OK;
+        idx += accepted;
+        if (accepted == cs.size()) continue;                             // next round (or done)
+        // ---- member idx did not validate: decode it the sequential way, then resynchronise on the candidate list
+        bool crc_error = false;
+        int st = gzip_member(in, n, d_in, off, o, &crc_error);
+        if (st) return st;
+        ends.push_back(o.len);
+        if (crc_error) { *result = SWC_GZIP_WRONG_CRC; *stop = true; return SWC_OK; }
+        idx = (size_t)(std::lower_bound(pos.begin(), pos.end(), *off) - pos.begin());
+    }
     return SWC_OK;
 }
 
 int upload(DevBuf &d, const uint8_t *in, size_t n) {
     int st = d.alloc(round16(n) + 32);
     if (st) return st;
-    if (n) SWC_CUDA_TRY(cudaMemcpy(d.p, in, n, cudaMemcpyHostToDevice));
-    return SWC_OK;
+    return copy_pageable(d.p, in, n, true);
 }
 
 template <typename F>
@@ -158,11 +305,11 @@ int32_t swc_gzip_unarchive(const uint8_t *in, size_t in_len, uint8_t **out, size
     DevBuf d_in;
     int st = upload(d_in, in, in_len);
     if (st) return st;
-    std::vector<uint8_t> o;
+    HostOut o;
     size_t off = 0; bool crc_error = false;
     if ((st = gzip_member(in, in_len, d_in.as<u8>(), &off, o, &crc_error))) return st;
     if (consumed_bytes) *consumed_bytes = off;
-    if ((st = give(o, out, out_len))) return st;
+    if ((st = o.release_to(out, out_len))) return st;
     return crc_error ? SWC_GZIP_WRONG_CRC : SWC_OK;
 }
 
@@ -174,17 +321,19 @@ int32_t swc_gzip_multi_unarchive(const uint8_t *in, size_t in_len,
     DevBuf d_in;
     int st = upload(d_in, in, in_len);
     if (st) return st;
-    std::vector<uint8_t> o;
+    HostOut o;
     std::vector<size_t> ends;
     size_t off = 0;
     int result = SWC_OK;
-    while (off < in_len) {
+    bool stop = false;
+    if ((st = gzip_multi_batch(in, in_len, d_in.as<u8>(), o, ends, &off, &result, &stop))) return st;
+    while (off < in_len && !stop) {
         bool crc_error = false;
         if ((st = gzip_member(in, in_len, d_in.as<u8>(), &off, o, &crc_error))) return st;
-        ends.push_back(o.size());
+        ends.push_back(o.len);
         if (crc_error) { result = SWC_GZIP_WRONG_CRC; break; }
     }
-    if ((st = give(o, out, out_len))) return st;
+    if ((st = o.release_to(out, out_len))) return st;
     *member_ends = (size_t *)swc_alloc(sizeof(size_t) * (ends.size() + 1));
     for (size_t i = 0; i < ends.size(); i++) (*member_ends)[i] = ends[i];
     *n_members = ends.size();

@@ -6,6 +6,8 @@
 // identity, which holds for the conditioned CRC values).  Adler-32 splits the same way.  xxHash32 and SHA-256 have no
 // combine operator, so they run one thread per buffer (many buffers in parallel for LZ4 block checksums).
 #include "common.cuh"
+#include <algorithm>
+#include <vector>
 #include "checks.cuh"
 
 namespace swc {
@@ -141,6 +143,103 @@ int crc32(const u8 *d, u64 n, u64 *d_result, u64 *d_partial, cudaStream_t s) { r
 int bzip2_crc32(const u8 *d, u64 n, u64 *d_result, u64 *d_partial, cudaStream_t s) { return run<1>(d, n, d_result, d_partial, s); }
 int crc64(const u8 *d, u64 n, u64 *d_result, u64 *d_partial, cudaStream_t s) { return run<2>(d, n, d_result, d_partial, s); }
 int adler32(const u8 *d, u64 n, u64 *d_result, u64 *d_partial, cudaStream_t s) { return run<3>(d, n, d_result, d_partial, s); }
+
+// ---------------------------------------------------------------- CRC-32 of many buffers: one warp per buffer
+// Each lane folds one of 32 contiguous segments with the byte table (shared memory), then the 32 conditioned values are
+// chained with x^(8*len) multiplications — the same identity as above, inside one warp.
+__global__ void __launch_bounds__(256) crc32_units_kernel(const u8 *base, const u64 *off, const u64 *len, u32 *result, u64 n) {
+    __shared__ u32 tab[256];
+    for (u32 i = threadIdx.x; i < 256; i += blockDim.x) { u32 c = i; for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1; tab[i] = c; }
+    __syncthreads();
+    const u64 unit = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (unit >= n) return;
+    const u32 lane = threadIdx.x & 31;
+    const u8 *p = base + off[unit];
+    const u64 L = len[unit];
+    const u64 seg = (L + 31) / 32;
+    const u64 sb = lane * seg < L ? lane * seg : L, se = sb + seg < L ? sb + seg : L;
+    u32 c = 0xFFFFFFFFu;
+    for (u64 i = sb; i < se; i++) c = tab[(c ^ p[i]) & 0xFF] ^ (c >> 8);
+    c = ~c;
+    const u32 pw = xpow32r(seg);
+    u32 acc = __shfl_sync(0xFFFFFFFFu, c, 0);
+    for (int l = 1; l < 32; l++) {
+        const u32 pl = __shfl_sync(0xFFFFFFFFu, c, l);
+        const u64 lb = (u64)l * seg < L ? (u64)l * seg : L, le = lb + seg < L ? lb + seg : L;
+        if (le == lb) continue;
+        acc = mulmod32r(le - lb == seg ? pw : xpow32r(le - lb), acc) ^ pl;
+    }
+    if (lane == 0) result[unit] = acc;
+}
+
+int crc32_units(const u8 *base, const u64 *off, const u64 *len, u32 *result, u64 n, cudaStream_t s) {
+    if (!n) return SWC_OK;
+    crc32_units_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(base, off, len, result, n);
+    count_launch();
+    SWC_CUDA_TRY(cudaGetLastError());
+    return SWC_OK;
+}
+
+// gzip member signature scan (GzipHeader.swift:70-81: magic 1f 8b, method 8, reserved flag bits clear); positions are
+// appended in any order and sorted by the host wrapper
+__global__ void __launch_bounds__(256) gzip_scan_kernel(const u8 *d, u64 n, u64 *list, unsigned long long *count, u64 cap) {
+    const u64 base = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (base >= n) return;
+    // 16 positions per thread from one aligned 16-byte load plus the 3 bytes that follow
+    const uint4 v = *(const uint4 *)(d + base);                       // the buffer is padded by >= 32 bytes
+    const u32 w[5] = {v.x, v.y, v.z, v.w, *(const u32 *)(d + base + 16)};
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const u32 x = __funnelshift_r(w[i >> 2], w[(i >> 2) + 1], (i & 3) * 8);
+        if ((x & 0xE0FFFFFFu) == 0x00088B1Fu && base + i + 20 <= n) {
+            const u64 slot = atomicAdd(count, 1ull);
+            if (slot < cap) list[slot] = base + i;
+        }
+    }
+}
+
+int find_gzip_members(const u8 *d_in, u64 n, std::vector<size_t> &pos) {
+    pos.clear();
+    if (n < 20) return SWC_OK;
+    const u64 cap = 1u << 22;
+    void *p = nullptr;
+    int st = arena_get(2, 256 + cap * 8, &p, 0);
+    if (st) return st;
+    unsigned long long *count = (unsigned long long *)p;
+    u64 *list = (u64 *)((u8 *)p + 256);
+    SWC_CUDA_TRY(cudaMemsetAsync(count, 0, 8, 0));
+    const u64 threads = (n + 15) / 16;
+    gzip_scan_kernel<<<(unsigned)((threads + 255) / 256), 256>>>(d_in, n, list, count, cap);
+    count_launch();
+    SWC_CUDA_TRY(cudaGetLastError());
+    unsigned long long h = 0;
+    SWC_CUDA_TRY(cudaMemcpy(&h, count, 8, cudaMemcpyDeviceToHost));
+    if (h > cap) return SWC_OK;                                       // absurd candidate count: caller walks sequentially
+    std::vector<u64> tmp(h);
+    if (h) SWC_CUDA_TRY(cudaMemcpy(tmp.data(), list, h * 8, cudaMemcpyDeviceToHost));
+    std::sort(tmp.begin(), tmp.end());
+    pos.assign(tmp.begin(), tmp.end());
+    return SWC_OK;
+}
+
+// gather: unit i's bytes [src_off[i], +len[i]) -> dst[dst_off[i] ...), one warp per unit
+__global__ void __launch_bounds__(256) gather_units_kernel(const u8 *src, const u64 *src_off, const u64 *len, u8 *dst, const u64 *dst_off, u64 n) {
+    const u64 unit = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (unit >= n) return;
+    const u32 lane = threadIdx.x & 31;
+    const u8 *s = src + src_off[unit];
+    u8 *d = dst + dst_off[unit];
+    const u64 L = len[unit];
+    for (u64 i = lane; i < L; i += 32) d[i] = s[i];
+}
+
+int gather_units(const u8 *src, const u64 *src_off, const u64 *len, u8 *dst, const u64 *dst_off, u64 n, cudaStream_t s) {
+    if (!n) return SWC_OK;
+    gather_units_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(src, src_off, len, dst, dst_off, n);
+    count_launch();
+    SWC_CUDA_TRY(cudaGetLastError());
+    return SWC_OK;
+}
 
 // ---------------------------------------------------------------- xxHash32 (seed 0), one thread per buffer
 #define XP1 0x9E3779B1u

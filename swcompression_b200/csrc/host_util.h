@@ -43,7 +43,16 @@ struct UnitResult {
 // Deflate stream starting at byte `start` + `start_bit` bits inside d_in[0..in_len)
 int deflate_unit_device(const u8 *d_in, size_t in_len, size_t start_bit_abs, UnitResult &r, size_t hint = 0);
 
+// batched Deflate on device-resident tables (api_deflate.cu); scratch == nullptr -> library pool
+int deflate_batch_impl(const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len, const uint8_t *start_bits,
+                       uint8_t *out_base, const uint64_t *out_off, const uint64_t *out_cap, uint64_t out_total,
+                       uint64_t *out_len, uint64_t *consumed_bits, int32_t *status, uint64_t n,
+                       void *scratch, size_t scratch_bytes, cudaStream_t stream);
+
 inline size_t round16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+// large transfers between pageable host memory and the device: T threads x (stream + two pinned bounce buffers) (runtime.cu)
+int copy_pageable(void *dst, const void *src, size_t bytes, bool to_device);
 
 // hand a device buffer back to a C caller as swc_alloc'ed host memory
 int to_host_alloc(const void *d, size_t n, uint8_t **out, size_t *out_len);

@@ -72,3 +72,65 @@ def test_gzip_zlib_roundtrip_errors_and_payloads(gpu, oracle):
             with pytest.raises(gpu.SWCompressionError) as e:
                 fn(cut)
             assert e.value.code == ost
+
+
+def _members(rng, count):
+    """count gzip members of mixed size/shape: empty, named, stored payloads holding the member signature, text."""
+    raws, blobs = [], []
+    for i in range(count):
+        kind = i % 7
+        if kind == 0:
+            raw = b""
+        elif kind == 1:
+            raw = (b"\x1f\x8b\x08\x00" + bytes(rng.randrange(256) for _ in range(40))) * 30   # look-alike signatures
+        else:
+            raw = H.textlike(rng.randrange(1, 70000), 100 + i)
+        level = 0 if kind == 1 else rng.choice((1, 6, 9))
+        blob = gzip.compress(raw, level)
+        if kind == 3:                                  # FNAME header
+            blob = blob[:3] + b"\x08" + blob[4:10] + b"member-%d\x00" % i + blob[10:]
+        raws.append(raw)
+        blobs.append(blob)
+    return raws, blobs
+
+
+def test_gzip_multi_member_batch_matches_oracle(gpu, oracle):
+    """Many-member archives take the batched path (signature scan + speculative decode + in-order validation); the result,
+    the error case and the members returned with it must equal the sequential reference walk (GzipArchive.swift:52-77)."""
+    rng = random.Random(77)
+    raws, blobs = _members(rng, 60)
+    data = b"".join(blobs)
+    ost, oparts, _ = oracle.gzip_multi_unarchive(data)
+    assert ost == 0 and oparts == raws
+    assert gpu.GzipArchive.multiUnarchive(data) == raws
+    # wrong CRC in member 17: members 0..17 are returned with the error
+    bad = list(blobs)
+    b = bytearray(bad[17]); b[-8] ^= 0x40; bad[17] = bytes(b)
+    data = b"".join(bad)
+    ost, oparts, _ = oracle.gzip_multi_unarchive(data)
+    with pytest.raises(gpu.GzipError) as e:
+        gpu.GzipArchive.multiUnarchive(data)
+    assert e.value.code == ost and e.value.case == "wrongCRC" and e.value.payload == oparts == raws[:18]
+    # wrong ISIZE in member 30, damaged payload in member 5, trailing garbage, truncation: same error as the oracle
+    variants = []
+    b = bytearray(blobs[30]); b[-1] ^= 1
+    variants.append(b"".join(blobs[:30]) + bytes(b) + b"".join(blobs[31:]))
+    b = bytearray(blobs[5]); b[len(b) // 2] ^= 0xFF
+    variants.append(b"".join(blobs[:5]) + bytes(b) + b"".join(blobs[6:]))
+    variants.append(b"".join(blobs) + b"\x00" * 7)
+    variants.append(b"".join(blobs) + b"\x1f\x8b\x08\x00" + b"\x00" * 30)
+    variants.append(b"".join(blobs)[:-3])
+    for v in variants:
+        ost, oparts, _ = oracle.gzip_multi_unarchive(v)
+        if ost == 0:
+            assert gpu.GzipArchive.multiUnarchive(v) == oparts
+        else:
+            with pytest.raises(gpu.SWCompressionError) as e:
+                gpu.GzipArchive.multiUnarchive(v)
+            assert e.value.code == ost
+    # BGZF-shaped archive: 3000 members of <= 64 KiB (thread-per-member kernel would need >= 20000; this is the warp kernel)
+    pool = [gzip.compress(H.textlike(rng.randrange(20000, 65536), 900 + i), 6) for i in range(24)]
+    praw = [gzip.decompress(p) for p in pool]
+    order = [rng.randrange(24) for _ in range(3000)]
+    got = gpu.GzipArchive.multiUnarchive(b"".join(pool[i] for i in order))
+    assert len(got) == 3000 and all(got[j] == praw[order[j]] for j in range(3000))

@@ -32,7 +32,10 @@ constexpr int W_CL_BO = 133;     // [1..7]
 constexpr int W_TOTAL = 141;     // 564 B per lane -> 12 resident warps per SM
 constexpr int WARPS_PER_CTA = 4;
 constexpr int CTAS_PER_SM = 3;
-constexpr int KLIT = 4;          // lit/len symbols a lane may decode per round before the warp services pending matches
+#ifndef SWC_KLIT
+#define SWC_KLIT 4
+#endif
+constexpr int KLIT = SWC_KLIT;          // lit/len symbols a lane may decode per round before the warp services pending matches
 constexpr int SMEM_LUT_WORDS = 64;   // CTA-shared length/distance base+extra tables
 constexpr size_t SMEM_BYTES = (size_t)WARPS_PER_CTA * W_TOTAL * 32 * 4 + SMEM_LUT_WORDS * 4;
 
@@ -372,29 +375,33 @@ __device__ __forceinline__ int begin_block(BitReader &br, Emitter &em, u32 *S, B
     return SWC_OK;
 }
 
-// One lit/len symbol (Deflate.swift:171-198). Literals are emitted; a length symbol reads its extra bits, leaves the
-// match length in `pend_len` and moves the lane to ST_MATCH. Returns SWC_OK or the reference's error.
-__device__ __forceinline__ int litlen_step(BitReader &br, Emitter &em, const u32 *S, const BlockCtx &bc, const u32 *lut,
-                                           int &state, u32 &pend_len) {
+// One lit/len symbol (Deflate.swift:171-198). Literals are emitted; any other symbol (end-of-block or a length) is only
+// parked in `pend_sym` and the lane moves to ST_MATCH: the rare tail (EOB test, range test, length extra bits) then runs once
+// per round in match_step with every parked lane taking part, instead of in each of the KLIT steps with ~4 of 32 lanes
+// (ncu source view: that tail was 9.8 % of all issued instructions at 3.7 active threads).
+__device__ __forceinline__ int litlen_step(BitReader &br, Emitter &em, const u32 *S, const BlockCtx &bc,
+                                           int &state, u32 &pend_sym) {
     br.need32();
     int L;
     const int sym = decode_symbol<0>(br, bc.lit_lim, S + W_LIT_BO * 32, S + W_LIT_SYM * 32, L);
     if (sym < 0 || br.avail < L) return SWC_DEFLATE_SYMBOL_NOT_FOUND;
     br.skip(L);
     if (sym < 256) { em.literal((u32)sym); return SWC_OK; }
-    if (sym == 256) { state = bc.is_last ? ST_DONE : ST_HEADER; return SWC_OK; }
-    if (sym > 285) return SWC_DEFLATE_WRONG_SYMBOL;
-    const u32 le = lut[sym - 257];
-    const int eb = (int)(le >> 16);
-    if (br.avail < eb) return SWC_DEFLATE_SYMBOL_NOT_FOUND;
-    pend_len = (le & 0xFFFFu) + br.peek(eb);
-    br.skip(eb);
+    pend_sym = (u32)sym;
     state = ST_MATCH;
     return SWC_OK;
 }
 
 // Distance half of a match (Deflate.swift:199-232).
-__device__ __forceinline__ int dist_step(BitReader &br, Emitter &em, const u32 *S, const BlockCtx &bc, const u32 *lut, u32 length) {
+__device__ __forceinline__ int dist_step(BitReader &br, Emitter &em, const u32 *S, const BlockCtx &bc, const u32 *lut,
+                                         int &state, u32 sym) {
+    if (sym == 256) { state = bc.is_last ? ST_DONE : ST_HEADER; return SWC_OK; }
+    if (sym > 285) return SWC_DEFLATE_WRONG_SYMBOL;
+    const u32 le = lut[sym - 257];
+    const int eb = (int)(le >> 16);                                // <= 5 bits: still inside the 33 bits need32() gave the symbol
+    if (br.avail < eb) return SWC_DEFLATE_SYMBOL_NOT_FOUND;
+    const u32 length = (le & 0xFFFFu) + br.peek(eb);
+    br.skip(eb);
     br.need32();
     int DL;
     const int dsym = decode_symbol<1>(br, bc.dst_lim, S + W_DST_BO * 32, S + W_DST_SYM * 32, DL);
@@ -474,14 +481,14 @@ inflate_huffman_kernel(BatchArgs a) {
 #pragma unroll 1
         for (int k = 0; k < KLIT; k++) {
             if (state == ST_SYMBOLS) {
-                const int r = litlen_step(br, em, S, bc, lut, state, pend_len);
+                const int r = litlen_step(br, em, S, bc, state, pend_len);
                 if (r) { status = r; state = ST_DONE; }
             }
         }
         if (state == ST_MATCH) {
-            const int r = dist_step(br, em, S, bc, lut, pend_len);
+            const int r = dist_step(br, em, S, bc, lut, state, pend_len);
             if (r) { status = r; state = ST_DONE; }
-            else state = ST_SYMBOLS;
+            else if (state == ST_MATCH) state = ST_SYMBOLS;
         } else if (state == ST_HEADER) {
             int next = ST_DONE;
             const int r = begin_block(br, em, S, bc, next);

@@ -189,3 +189,33 @@ def test_batch_host_pipelined(oracle):
         for i in range(0, n, 97):
             ost, oout, oused = oracle.deflate_decompress(units[i])
             assert bytes(out[i * cap:i * cap + int(r_len[i])]) == oout == raws[i % 64] and r_used[i] == oused
+
+
+def test_large_batch_thread_kernel_with_overlapped_resolve(oracle):
+    """>= 20000 units take the thread-per-unit K1 with K2 following it on a second stream (inflate.cu launch()): valid,
+    stored, truncated, corrupted, over-subscribed (slow kernel) and empty units side by side, all equal to the oracle."""
+    rng = random.Random(17)
+    distinct = []
+    for i in range(40):
+        distinct.append(H.raw_deflate(H.textlike(rng.randrange(200, 9000), 300 + i), rng.choice((1, 6, 9))))
+    distinct.append(H.raw_deflate(H.textlike(4000, 350), 0))                     # stored blocks
+    distinct.append(H.raw_deflate(b""))
+    distinct.append(H.raw_deflate(bytes(7000)))                                  # one long overlapping match chain
+    good = list(distinct)
+    for d in good[:12]:
+        distinct.append(d[:rng.randrange(1, len(d))])                             # truncated
+        b = bytearray(d)
+        b[rng.randrange(min(len(b), 60))] ^= 1 << rng.randrange(8)                # damaged header / early payload
+        distinct.append(bytes(b))
+    expect = [oracle.deflate_decompress(u) for u in distinct]
+    n = 24576
+    order = [rng.randrange(len(distinct)) for _ in range(n)]
+    st, ln, used, outs = run_batch([distinct[i] for i in order], 16384)
+    for j, i in enumerate(order):
+        ost, oout, oused = expect[i]
+        if ost == 0 and len(oout) > 16384:
+            assert st[j] == 1 and ln[j] == len(oout)
+        elif ost == 0:
+            assert st[j] == 0 and outs[j] == oout and used[j] == oused, (j, i, st[j])
+        else:
+            assert st[j] == ost, (j, i, st[j], ost)

@@ -191,8 +191,8 @@ def test_batch_host_pipelined(oracle):
             assert bytes(out[i * cap:i * cap + int(r_len[i])]) == oout == raws[i % 64] and r_used[i] == oused
 
 
-def test_large_batch_thread_kernel_with_overlapped_resolve(oracle):
-    """>= 20000 units take the thread-per-unit K1 with K2 following it on a second stream (inflate.cu launch()): valid,
+def test_large_batch_thread_kernel(oracle):
+    """>= 20000 units take the thread-per-unit K1 (persistent lanes, ticket counter; inflate.cu launch()): valid,
     stored, truncated, corrupted, over-subscribed (slow kernel) and empty units side by side, all equal to the oracle."""
     rng = random.Random(17)
     distinct = []

@@ -301,7 +301,7 @@ def run_product(args):
         e2e = {"value": out_total * world / float(tt.item()) / 1e9, "unit": "GB/s",
                "h2d_bytes_per_step": int(in_total + n_e * 8 * 4), "d2h_bytes_per_step": int(out_total + n_e * 20),
                "units_per_step": int(n_e), "ms_per_step": float(tt.item()) * 1e3,
-               "api": "swc_deflate_decompress_batch_host (pinned host buffers; per call: H2D + K1/K2 + D2H, 8 slices pipelined over 3 streams)"}
+               "api": "swc_deflate_decompress_batch_host (pinned host buffers; per call: H2D + K1/K2 + D2H, up to 32 slices of >= 2048 units pipelined over 3 streams)"}
         L.swc_free_pinned(C.c_void_p(p_in)); L.swc_free_pinned(C.c_void_p(p_out))
 
     cpu = None

@@ -172,6 +172,11 @@ struct Emit {
 };
 
 // One match: length extra bits + distance symbol + distance extra bits (Deflate.swift:186-232). Returns an error or 0.
+#ifndef SWC_KW_LIT
+#define SWC_KW_LIT 4
+#endif
+constexpr int KW_LIT = SWC_KW_LIT;      // lit/len steps per round before pending matches are serviced
+
 template <bool EMIT>
 __device__ __forceinline__ int window_match(const Smem &S, const Tables &T, const u32 *lens_tab, Cursor &c, u32 &p, u64 left,
                                             u32 value, int eb, Emit *em, u32 &length_out) {
@@ -220,45 +225,58 @@ __device__ __forceinline__ WinResult decode_window(const Smem &S, const Tables &
     bool eob = false;
     bool active = enable;
     if (enable) { r.nbytes = 0; r.nrec = 0; r.head = 0; r.tail = 0; r.flags = 0; c.init(S.stage, start + stage_bit0); }
+    // A round = up to KW_LIT lit/len symbols per lane, then ONE pass of the (long, rare) match path for every lane that
+    // parked a length symbol — the same scheme as the thread-per-unit kernel (inflate.cu): the match path used to run inside
+    // every step with ~4 of 32 lanes (22 % of the issued instructions, ncu source view).
+    bool pend = false;
+    u32 pvalue = 0; int peb = 0;
     while (__any_sync(SWC_FULL, active)) {
-        if (active) {
-            c.need(S.stage);
-            const u32 e = S.lit_lut[c.peek(LIT_BITS)];
-            int L = (int)(e & 15);
-            int kind = (int)((e >> 4) & 3);
-            u32 value = e >> 16;
-            int eb = (int)((e >> 6) & 15);
-            if (e & E_SLOW) {
-                const int sym = canon_decode<0>(S, T.lit_lim, c.peek(15), L);
-                if (sym < 0) err = SWC_DEFLATE_SYMBOL_NOT_FOUND;
-                else if (sym < 256) { kind = 0; value = (u32)sym; eb = 0; }
-                else if (sym == 256) { kind = 1; eb = 0; }
-                else if (sym > 285) { kind = 3; }
-                else { kind = 2; const u32 le = lens_tab[sym - 257]; value = le & 0xFFFFu; eb = (int)(le >> 16); }
-            }
-            if (!err && (u64)p + (u32)L > left) err = SWC_DEFLATE_SYMBOL_NOT_FOUND;
-            if (!err) {
-                c.skip(L); p += (u32)L;
-                if (kind == 0) {
-                    if (EMIT) em->literal(value);
-                    r.nbytes++; run++;
-                } else if (kind == 1) {
-                    eob = true;
-                } else if (kind == 3) {
-                    err = SWC_DEFLATE_WRONG_SYMBOL;
-                } else {
-                    u32 length = 0;
-                    err = window_match<EMIT>(S, T, lens_tab, c, p, left, value, eb, em, length);
-                    if (!err) {
-                        if (!has_match) { r.head = run; has_match = true; }
-                        else if (run > 255) r.nrec++;             // escape record in front of a later match of this window
-                        r.nrec++;
-                        r.nbytes += length;
-                        run = 0;
+#pragma unroll 1
+        for (int k = 0; k < KW_LIT; k++) {
+            if (active && !pend) {
+                c.need(S.stage);
+                const u32 e = S.lit_lut[c.peek(LIT_BITS)];
+                int L = (int)(e & 15);
+                int kind = (int)((e >> 4) & 3);
+                u32 value = e >> 16;
+                int eb = (int)((e >> 6) & 15);
+                if (e & E_SLOW) {
+                    const int sym = canon_decode<0>(S, T.lit_lim, c.peek(15), L);
+                    if (sym < 0) err = SWC_DEFLATE_SYMBOL_NOT_FOUND;
+                    else if (sym < 256) { kind = 0; value = (u32)sym; eb = 0; }
+                    else if (sym == 256) { kind = 1; eb = 0; }
+                    else if (sym > 285) { kind = 3; }
+                    else { kind = 2; const u32 le = lens_tab[sym - 257]; value = le & 0xFFFFu; eb = (int)(le >> 16); }
+                }
+                if (!err && (u64)p + (u32)L > left) err = SWC_DEFLATE_SYMBOL_NOT_FOUND;
+                if (!err) {
+                    c.skip(L); p += (u32)L;
+                    if (kind == 0) {
+                        if (EMIT) em->literal(value);
+                        r.nbytes++; run++;
+                    } else if (kind == 1) {
+                        eob = true;
+                    } else if (kind == 3) {
+                        err = SWC_DEFLATE_WRONG_SYMBOL;
+                    } else {
+                        pend = true; pvalue = value; peb = eb;
                     }
                 }
+                if (err || eob || (!pend && p >= hi)) active = false;
             }
-            if (err || eob || p >= hi) active = false;
+        }
+        if (active && pend) {
+            u32 length = 0;
+            err = window_match<EMIT>(S, T, lens_tab, c, p, left, pvalue, peb, em, length);
+            if (!err) {
+                if (!has_match) { r.head = run; has_match = true; }
+                else if (run > 255) r.nrec++;             // escape record in front of a later match of this window
+                r.nrec++;
+                r.nbytes += length;
+                run = 0;
+            }
+            pend = false;
+            if (err || p >= hi) active = false;
         }
     }
     if (enable) {

@@ -20,6 +20,8 @@ namespace bzip2 {
 constexpr int WARPS = 4;
 constexpr int MAX_SYMS = 258;
 constexpr int MAX_LEN = 20;
+constexpr int NCH = 4;           // chains a lane keeps in flight in the chase (8 measured slower: one warp is issue-latency-bound on the bookkeeping)
+constexpr int NSEG = 512;        // chain pieces of the inverse BWT (see the chase)
 
 struct WarpSmem {
     u16 syms[6][MAX_SYMS + 2];      // symbols sorted by (length, symbol) per table
@@ -82,8 +84,19 @@ struct Bits {
 // ---------------------------------------------------------------- register-resident MTF list (8 bytes per lane)
 __device__ __forceinline__ u32 mtf_front(u64 v) { return (u32)__shfl_sync(SWC_FULL, (u32)v, 0) & 0xFF; }
 // move element at index i (0..255) to the front; returns it
+// (the result is only meaningful on lane 0 when i < 8 — BwtOut::put() stores from lane 0; the general path returns it everywhere)
 __device__ __forceinline__ u32 mtf_move(u64 &v, u32 i) {
     const u32 lane = lane_id();
+    if (i < 8) {                                      // warp-uniform; ~2/3 of all symbols: the whole move stays inside lane 0's word
+        const u32 sh = i * 8;
+        const u64 e = (v >> sh) & 0xFF;
+        if (lane == 0) {
+            const u64 below = v & ((1ull << sh) - 1);                     // bytes 0..i-1
+            const u64 above = sh == 56 ? 0ull : (v >> (sh + 8)) << (sh + 8);
+            v = above | (below << 8) | e;
+        }
+        return (u32)e;
+    }
     const u32 q = i >> 3, r = i & 7;
     const u32 lo = (u32)v, hi = (u32)(v >> 32);
     const u32 src = r < 4 ? __shfl_sync(SWC_FULL, lo, q) : __shfl_sync(SWC_FULL, hi, q);
@@ -269,20 +282,23 @@ __global__ void __launch_bounds__(WARPS * 32) bzip2_kernel(Args a) {
             int decoded = 0, sel_idx = 1;
             int table = selectors[0];
             u32 my_limit = S.limit[table][lane];
+            const u32 *t_base = S.base[table];
+            const u16 *t_first = S.first[table], *t_syms = S.syms[table];
             u64 run_length = 0, repeat_power = 1;
             for (;;) {
                 if (decoded >= 50) {
                     if (sel_idx >= nsel) FAIL(SWC_BZIP2_WRONG_SELECTOR);
                     table = selectors[sel_idx++];
                     my_limit = S.limit[table][lane];
+                    t_base = S.base[table]; t_first = S.first[table]; t_syms = S.syms[table];
                     decoded = 0;
                 }
                 br.need32();
                 const u32 r20 = br.peek(20);
                 const int L = 1 + __popc(__ballot_sync(SWC_FULL, r20 >= my_limit));
                 if (L > MAX_LEN || br.avail < L) FAIL(SWC_BZIP2_SYMBOL_NOT_FOUND);
-                const u32 sidx = S.first[table][L] + ((r20 - S.base[table][L]) >> (20 - L));
-                const int symbol = S.syms[table][sidx];
+                const u32 sidx = t_first[L] + ((r20 - t_base[L]) >> (20 - L));
+                const int symbol = t_syms[sidx];
                 br.skip(L);
                 decoded++;
                 if (symbol < 2) {                                                    // RUNA / RUNB :226-230
@@ -297,9 +313,12 @@ __global__ void __launch_bounds__(WARPS * 32) bzip2_kernel(Args a) {
                     run_length = 0; repeat_power = 1;
                 }
                 if (symbol == used_count - 1) break;                                 // EOB :239
-                if (bo.n + 1 > scr_cap) FAIL(SWC_ERR_OUTPUT_OVERFLOW);
+                // capacity: put() only writes the shared staging line and flush() fences global stores, so the test is
+                // made once per 128-byte line (and once after the loop) instead of per symbol
+                if (bo.fill == 127 && bo.n + 1 > scr_cap) FAIL(SWC_ERR_OUTPUT_OVERFLOW);
                 bo.put(mtf_move(mtf, (u32)symbol - 1));                              // :243-245
             }
+            if (bo.n > scr_cap) FAIL(SWC_ERR_OUTPUT_OVERFLOW);
             // pad the staging line so the final flush writes whole words
             bo.flush();
         }
@@ -325,14 +344,17 @@ __global__ void __launch_bounds__(WARPS * 32) bzip2_kernel(Args a) {
                 u32 run = incl - sum;
                 for (int k = 0; k < 8; k++) { S.counts[lane * 8 + k] = run; run += loc[k]; }
                 __syncwarp();
-                // stable scatter: successor[base[c]++] = i, in increasing i — 32 positions per round, ranked with match_any
+                // stable scatter: successor[base[c]++] = i, in increasing i — 32 positions per round, ranked with match_any.
+                // Blocks of < 2^20 bytes (every block a bzip2 encoder can produce: <= 900 000) carry bwt[i] in bits 20..27 of
+                // the entry, so the chase below needs ONE dependent load per output byte instead of two.
+                const bool packed = n < (1u << 20);
                 for (u64 i0 = 0; i0 < n; i0 += 32) {
                     const u64 i = i0 + lane;
                     const bool act = i < n;
                     const u32 c = act ? bwt[i] : 0x100 + lane;
                     const u32 peers = __match_any_sync(SWC_FULL, c);
                     const u32 rank = __popc(peers & ((1u << lane) - 1));
-                    if (act) succ[S.counts[c] + rank] = (u32)i;
+                    if (act) succ[S.counts[c] + rank] = (u32)i | (packed ? c << 20 : 0u);   // entry = index i (+ bwt[i] when it fits)
                     __syncwarp();
                     if (act && rank == 0) S.counts[c] += __popc(peers);
                     __syncwarp();
@@ -341,58 +363,126 @@ __global__ void __launch_bounds__(WARPS * 32) bzip2_kernel(Args a) {
 #ifdef SWC_BZ_PROFILE
                 long long t_sort = clock64();
 #endif
-                // ---- pointer chase split over 32 lanes (splitter list ranking) ----
-                // splitter j starts at index s_j (s_0 = orig_ptr); bit 31 of succ[s_j] marks it.
+                // ---- pointer chase: list ranking over NSEG splitters, NCH chains in flight per lane ----
+                // The inverse BWT is one chain of n dependent loads (the reference walks it serially, BurrowsWheeler.swift:
+                // 52-62).  NSEG indices are marked as splitters (index 0 of the list = orig_ptr, the chain's origin); the
+                // chain pieces between splitters are independent, so lanes pull them from a queue — walk 1 measures each
+                // piece and finds the splitter that ends it, one lane then strings the pieces together from orig_ptr and
+                // gives each its output offset, walk 2 follows every piece again and writes its bytes.  Each lane keeps
+                // NCH pieces going at once (NCH independent loads in flight).  With 32 fixed pieces (the previous form) the
+                // longest piece was ~n/8 and ~6 lanes were busy on average (ncu source view).
                 const u32 MARK = 0x80000000u;
-                u32 my_start = lane == 0 ? orig_ptr : (u32)(((u64)lane * n) / 32);
-                // lanes whose start collides with an earlier lane's start sit out
-                bool owner = true;
-                for (int j = 0; j < 32; j++) { u32 sj = __shfl_sync(SWC_FULL, my_start, j); if (j < (int)lane && sj == my_start) owner = false; }
-                if (owner) S.split_len[lane] = 0;
-                __syncwarp();
-                if (owner) atomicOr(&succ[my_start], MARK);
-                __syncwarp();
-                // walk 1: length of my segment and which splitter ends it
-                u32 seg_len = 0, end_at = 0;
-                if (owner) {
-                    u32 cur = my_start;
-                    do { cur = succ[cur] & ~MARK; seg_len++; } while (!(succ[cur] & MARK) && seg_len < n);
-                    end_at = cur;
+                const u32 IDX = packed ? 0xFFFFFu : 0x7FFFFFFFu;
+                u32 *seg_len = (u32 *)&S.syms[0][0];                 // the Huffman tables are dead until the next block
+                u32 *seg_off = seg_len + NSEG;
+                u16 *seg_next = (u16 *)&S.counts[0];                 // so are the bucket counters
+                static_assert(sizeof(u32) * 2 * NSEG <= sizeof(S.syms) + sizeof(S.limit) + sizeof(S.base), "segment tables must fit the table area");
+                static_assert(sizeof(u16) * NSEG <= sizeof(S.counts), "segment links must fit the counter area");
+                const u32 nseg = n < 4096 ? 1u : (u32)NSEG;          // tiny blocks: one chain
+                auto seg_start = [&](u32 j) -> u32 { return j == 0 ? orig_ptr : (u32)(((u64)j * n) / nseg); };
+                // a regular splitter that coincides with orig_ptr is dropped (piece 0 owns that index); distinct j >= 1 give
+                // distinct indices because n >= 4096 > nseg
+                for (u32 j = lane; j < nseg; j += 32) {
+                    const bool dup = j != 0 && seg_start(j) == orig_ptr;
+                    seg_len[j] = dup ? 0xFFFFFFFFu : 0u;             // 0xFFFFFFFF = not a piece
+                    seg_off[j] = 0xFFFFFFFFu;                        // not on the path from orig_ptr (yet)
+                    seg_next[j] = 0xFFFF;
+                    if (!dup) atomicOr(&succ[seg_start(j)], MARK);
                 }
-                // map end index -> owning lane
-                u32 next_lane = 0xFFFFFFFFu;
-                for (int j = 0; j < 32; j++) {
-                    u32 sj = __shfl_sync(SWC_FULL, my_start, j);
-                    bool oj = __shfl_sync(SWC_FULL, (u32)owner, j) != 0;
-                    if (owner && oj && sj == end_at && next_lane == 0xFFFFFFFFu) next_lane = j;
-                }
-                // lane 0 order: follow segments from splitter 0 assigning output offsets until n bytes are covered
-                // (the path from orig_ptr is a cycle of length C <= n; when C < n the output wraps around it)
-                u64 my_off = ~0ull, cycle = 0;
+                if (lane == 0) S.stage[0] = 0;                       // piece queue head
+                __syncwarp();
+                __threadfence_block();
+                auto end_to_seg = [&](u32 e) -> u32 {                // which piece starts at index e (e is a marked index)
+                    if (e == orig_ptr) return 0;
+                    const u32 j = (u32)(((u64)e * nseg + n - 1) / n);
+                    return (j < nseg && seg_start(j) == e) ? j : 0xFFFFu;
+                };
+                // walk 1: piece lengths and links
                 {
-                    u32 curl = 0; u64 off = 0;
-                    for (int step = 0; step < 32; step++) {
-                        const u32 sl = __shfl_sync(SWC_FULL, seg_len, curl);
-                        const u32 nl = __shfl_sync(SWC_FULL, next_lane, curl);
-                        if (lane == curl && my_off == ~0ull) my_off = off;
-                        off += sl;
-                        if (nl == 0 || nl == 0xFFFFFFFFu) { cycle = off; break; }
-                        curl = nl;
-                        if (step == 31) cycle = off;
+                    u32 id[NCH], cur[NCH], k[NCH];
+#pragma unroll
+                    for (int q = 0; q < NCH; q++) id[q] = 0xFFFFFFFEu; // needs a piece
+                    bool more = true;
+                    for (;;) {
+                        bool any = false;
+#pragma unroll
+                        for (int q = 0; q < NCH; q++) {
+                            while (id[q] == 0xFFFFFFFEu && more) {   // pull the next real piece
+                                const u32 j = atomicAdd(&S.stage[0], 1u);
+                                if (j >= nseg) { more = false; break; }
+                                if (seg_len[j] != 0xFFFFFFFFu) { id[q] = j; cur[q] = seg_start(j); k[q] = 0; }
+                            }
+                            if (id[q] == 0xFFFFFFFEu) id[q] = 0xFFFFFFFFu;   // nothing left for this slot
+                            any |= id[q] != 0xFFFFFFFFu;
+                        }
+                        if (!__any_sync(SWC_FULL, any)) break;     // vote-driven: the lanes stay converged
+                        u32 v[NCH];
+#pragma unroll
+                        for (int q = 0; q < NCH; q++) v[q] = id[q] != 0xFFFFFFFFu ? succ[cur[q]] : 0u;
+#pragma unroll
+                        for (int q = 0; q < NCH; q++) {
+                            if (id[q] == 0xFFFFFFFFu) continue;
+                            if ((k[q] > 0 && (v[q] & MARK)) || k[q] >= n) {          // cur is the next splitter: piece complete
+                                seg_len[id[q]] = k[q];
+                                seg_next[id[q]] = (u16)end_to_seg(cur[q]);
+                                id[q] = 0xFFFFFFFEu;
+                            } else {
+                                cur[q] = v[q] & IDX; k[q]++;
+                            }
+                        }
                     }
                 }
+                __syncwarp();
+                // string the pieces together from orig_ptr (the path is a cycle of length C <= n; when C < n the output wraps)
+                u64 cycle = 0;
+                if (lane == 0) {
+                    u32 j = 0; u64 off = 0;
+                    for (u32 step = 0; step < nseg; step++) {
+                        seg_off[j] = (u32)off;
+                        off += seg_len[j];
+                        const u32 nx = seg_next[j];
+                        if (nx == 0 || nx >= nseg || seg_off[nx] != 0xFFFFFFFFu) break;
+                        j = nx;
+                    }
+                    cycle = off;
+                    S.stage[0] = 0;
+                }
                 cycle = __shfl_sync(SWC_FULL, cycle, 0);
-                // walk 2: emit my segment at my_off (+ k*cycle while < n). Output of this stage overwrites nothing it reads:
-                // it goes to `out + op` region?  No — RLE1 still has to expand it, so it is written back over... a second buffer:
-                // the low half of the successor array is dead after the walk, so the text goes to `text` = (u8*)succ + 4n.
-                // (scr layout keeps 4*scr_cap bytes there; text needs n <= scr_cap bytes placed after the live entries.)
+                __syncwarp();
+                // walk 2: emit.  The low half of the scratch after the successor array holds the text (RLE1 still has to
+                // expand it): text = selectors + 32768 + 16.
                 u8 *text = selectors + 32768 + 16;
-                if (owner && my_off != ~0ull) {
-                    u32 cur = my_start;
-                    for (u32 k = 0; k < seg_len; k++) {
-                        cur = succ[cur] & ~MARK;
-                        const u8 ch = bwt[cur];
-                        for (u64 pos = my_off + k; pos < n; pos += cycle) text[pos] = ch;
+                if (cycle > 0) {
+                    u32 id[NCH], cur[NCH], k[NCH], len[NCH], off[NCH];
+#pragma unroll
+                    for (int q = 0; q < NCH; q++) id[q] = 0xFFFFFFFEu;
+                    bool more = true;
+                    for (;;) {
+                        bool any = false;
+#pragma unroll
+                        for (int q = 0; q < NCH; q++) {
+                            while (id[q] == 0xFFFFFFFEu && more) {
+                                const u32 j = atomicAdd(&S.stage[0], 1u);
+                                if (j >= nseg) { more = false; break; }
+                                if (seg_len[j] != 0xFFFFFFFFu && seg_off[j] != 0xFFFFFFFFu && seg_len[j] != 0) {
+                                    id[q] = j; cur[q] = seg_start(j); k[q] = 0; len[q] = seg_len[j]; off[q] = seg_off[j];
+                                }
+                            }
+                            if (id[q] == 0xFFFFFFFEu) id[q] = 0xFFFFFFFFu;
+                            any |= id[q] != 0xFFFFFFFFu;
+                        }
+                        if (!__any_sync(SWC_FULL, any)) break;     // vote-driven: the lanes stay converged
+                        u32 v[NCH];
+#pragma unroll
+                        for (int q = 0; q < NCH; q++) v[q] = id[q] != 0xFFFFFFFFu ? succ[cur[q]] : 0u;
+#pragma unroll
+                        for (int q = 0; q < NCH; q++) {
+                            if (id[q] == 0xFFFFFFFFu) continue;
+                            cur[q] = v[q] & IDX;
+                            const u8 ch = packed ? (u8)(v[q] >> 20) : bwt[cur[q]];
+                            for (u64 pos = (u64)off[q] + k[q]; pos < n; pos += cycle) text[pos] = ch;
+                            if (++k[q] == len[q]) id[q] = 0xFFFFFFFEu;
+                        }
                     }
                 }
                 __syncwarp();

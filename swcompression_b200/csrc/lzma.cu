@@ -66,13 +66,15 @@ struct Dec {
         return b;
     }
     __device__ __forceinline__ int bit(u16 *prob) {               // LZMARangeDecoder.swift:65-80
+        // select form (no branch on the decoded bit: the warp runs one dependent chain, a taken branch costs several issue slots)
         const u32 p = *prob;
         const u32 bound = (range >> 11) * p;
-        int sym;
-        if (code < bound) { *prob = (u16)(p + ((2048 - p) >> 5)); range = bound; sym = 0; }
-        else { *prob = (u16)(p - (p >> 5)); code -= bound; range -= bound; sym = 1; }
+        const bool one = code >= bound;
+        *prob = (u16)(one ? p - (p >> 5) : p + ((2048 - p) >> 5));
+        range = one ? range - bound : bound;
+        code = one ? code - bound : code;
         if (range < TOP) { range <<= 8; code = (code << 8) | byte(); }
-        return sym;
+        return one ? 1 : 0;
     }
     __device__ __forceinline__ int direct(int count) {            // LZMARangeDecoder.swift:46-62
         u32 res = 0;
@@ -146,7 +148,10 @@ struct Dec {
                 const u32 prev = dict_end == dict_start ? 0 : prev_byte;
                 int symbol = 1;
                 u16 *lpz = lit + ((((u32)dict_end & lp_mask) << lc) + (prev >> (8 - lc))) * 0x300;
-                if (state >= 7) {
+                if (state < 7) {                                                      // plain literal: exactly 8 tree levels
+#pragma unroll
+                    for (int i = 0; i < 8; i++) symbol = (symbol << 1) | bit(&lpz[symbol]);
+                } else {
                     u32 match_byte = byte_at(rep0 + 1, oob);
                     if (oob) return SWC_ERR_REFERENCE_TRAP;
                     do {
@@ -156,8 +161,8 @@ struct Dec {
                         symbol = (symbol << 1) | b;
                         if (match_bit != b) break;
                     } while (symbol < 0x100);
+                    while (symbol < 0x100) symbol = (symbol << 1) | bit(&lpz[symbol]);
                 }
-                while (symbol < 0x100) symbol = (symbol << 1) | bit(&lpz[symbol]);
                 if (trap) return SWC_ERR_REFERENCE_TRAP;
                 usize -= 1;
                 put((u32)symbol - 0x100);
@@ -239,7 +244,14 @@ struct Dec {
                 __syncwarp();
                 prev_byte = dst[len - 1];
                 // dictStart bookkeeping of `len` put() calls
-                for (i64 i = 0; i < len; i++) { dict_end += 1; if (dict_end - dict_start == dict_size) dict_start += 1; }
+                // (closed form of: repeat len times { dict_end += 1; if (dict_end - dict_start == dict_size) dict_start += 1; } —
+                // the gap climbs to dict_size-1 and then every further byte advances dict_start; a gap that is already
+                // >= dict_size never meets the equality again)
+                {
+                    const i64 gap = dict_end - dict_start;
+                    if (gap < (i64)dict_size) { const i64 adv = gap + len - ((i64)dict_size - 1); if (adv > 0) dict_start += adv; }
+                    dict_end += len;
+                }
                 usize -= len;
             }
         }

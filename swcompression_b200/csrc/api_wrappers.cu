@@ -224,7 +224,7 @@ int gzip_multi_batch(const uint8_t *in, size_t n, const u8 *d_in, HostOut &o, st
             uint32_t *d_crc = (uint32_t *)(d_status + nu);
             if ((st = deflate_batch_impl(d_in, m, m + nu, nullptr, d_out.as<u8>(), m + 2 * nu, m + 3 * nu, out_total,
                                          m + 4 * nu, m + 5 * nu, d_status, nu, nullptr, 0, stream))) return st;
-            if ((st = checks::crc32_units(d_out.as<u8>(), m + 2 * nu, m + 4 * nu, d_crc, nu, stream))) return st;
+            if ((st = checks::crc32_units(d_out.as<u8>(), m + 2 * nu, m + 4 * nu, d_status, d_crc, nu, stream))) return st;
             SWC_CUDA_TRY(cudaMemcpyAsync(h_outlen.data(), m + 4 * nu, nu * 8, cudaMemcpyDeviceToHost, stream));
             SWC_CUDA_TRY(cudaMemcpyAsync(h_cons.data(), m + 5 * nu, nu * 8, cudaMemcpyDeviceToHost, stream));
             SWC_CUDA_TRY(cudaMemcpyAsync(h_status.data(), d_status, nu * 4, cudaMemcpyDeviceToHost, stream));

@@ -147,7 +147,7 @@ int adler32(const u8 *d, u64 n, u64 *d_result, u64 *d_partial, cudaStream_t s) {
 // ---------------------------------------------------------------- CRC-32 of many buffers: one warp per buffer
 // Each lane folds one of 32 contiguous segments with the byte table (shared memory), then the 32 conditioned values are
 // chained with x^(8*len) multiplications — the same identity as above, inside one warp.
-__global__ void __launch_bounds__(256) crc32_units_kernel(const u8 *base, const u64 *off, const u64 *len, u32 *result, u64 n) {
+__global__ void __launch_bounds__(256) crc32_units_kernel(const u8 *base, const u64 *off, const u64 *len, const int32_t *status, u32 *result, u64 n) {
     __shared__ u32 tab[256];
     for (u32 i = threadIdx.x; i < 256; i += blockDim.x) { u32 c = i; for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1; tab[i] = c; }
     __syncthreads();
@@ -155,7 +155,8 @@ __global__ void __launch_bounds__(256) crc32_units_kernel(const u8 *base, const 
     if (unit >= n) return;
     const u32 lane = threadIdx.x & 31;
     const u8 *p = base + off[unit];
-    const u64 L = len[unit];
+    // a unit that did not decode cleanly has no defined extent (Deflate reports the size it WOULD need on overflow): skip it
+    const u64 L = (status && status[unit] != SWC_OK) ? 0 : len[unit];
     const u64 seg = (L + 31) / 32;
     const u64 sb = lane * seg < L ? lane * seg : L, se = sb + seg < L ? sb + seg : L;
     u32 c = 0xFFFFFFFFu;
@@ -172,9 +173,9 @@ __global__ void __launch_bounds__(256) crc32_units_kernel(const u8 *base, const 
     if (lane == 0) result[unit] = acc;
 }
 
-int crc32_units(const u8 *base, const u64 *off, const u64 *len, u32 *result, u64 n, cudaStream_t s) {
+int crc32_units(const u8 *base, const u64 *off, const u64 *len, const int32_t *status, u32 *result, u64 n, cudaStream_t s) {
     if (!n) return SWC_OK;
-    crc32_units_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(base, off, len, result, n);
+    crc32_units_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(base, off, len, status, result, n);
     count_launch();
     SWC_CUDA_TRY(cudaGetLastError());
     return SWC_OK;

@@ -13,7 +13,7 @@ int crc64(const u8 *d, u64 n, u64 *d_result, u64 *d_partial, cudaStream_t s);
 int adler32(const u8 *d, u64 n, u64 *d_result, u64 *d_partial, cudaStream_t s);
 int xxh32_batch(const u8 *base, const u64 *off /* may be null */, const u64 *len, u32 *result, u64 n, cudaStream_t s);
 int sha256(const u8 *d, u64 n, u8 *d_digest, cudaStream_t s);
-int crc32_units(const u8 *base, const u64 *off, const u64 *len, u32 *result, u64 n, cudaStream_t s);   // warp per buffer
+int crc32_units(const u8 *base, const u64 *off, const u64 *len, const int32_t *status, u32 *result, u64 n, cudaStream_t s);   // warp per buffer; units with status != 0 are skipped (status may be null)
 int find_gzip_members(const u8 *d_in, u64 n, std::vector<size_t> &pos);   // sorted candidate member starts (device scan)
 int gather_units(const u8 *src, const u64 *src_off, const u64 *len, u8 *dst, const u64 *dst_off, u64 n, cudaStream_t s);
 

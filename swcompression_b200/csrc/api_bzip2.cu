@@ -4,6 +4,7 @@
 #include "../../include/swcgpu.h"
 #include "host_util.h"
 #include "bzip2.cuh"
+#include "checks.cuh"
 
 using namespace swc;
 
@@ -34,8 +35,111 @@ int bzip2_batch_impl(const uint8_t *in_base, const uint64_t *in_off, const uint6
     return bzip2::launch(a, stream);
 }
 
-// one stream starting at byte `start` of d_in; output grows until it fits
-int bzip2_unit_device(const u8 *d_in, size_t in_len, size_t start, UnitResult &r) {
+// 32 bits at an arbitrary bit position of the host copy, MSB first (BZip2's reader order)
+uint32_t bits32_at(const uint8_t *in, size_t in_len, uint64_t bitpos) {
+    uint64_t w = 0;
+    const size_t b0 = (size_t)(bitpos >> 3);
+    for (int k = 0; k < 5; k++) w = (w << 8) | (b0 + k < in_len ? in[b0 + k] : 0);
+    return (uint32_t)(w >> (8 - (bitpos & 7)));
+}
+
+// Block-parallel decode of ONE stream.  The blocks of a stream are independent once their starts are known, and the starts
+// are marked by a 48-bit magic — at any bit offset.  All magics are found by a device scan, every block candidate is decoded
+// as its own unit of one batched launch (block mode of the kernel), and the reference's sequential walk (BZip2.swift:66-95)
+// is kept as the validator: block k is accepted iff it decoded cleanly (including its CRC) and ended exactly at the next
+// magic; the walk must end on the end-of-stream magic with the right combined CRC.  Anything else (a look-alike magic, an
+// overflowing block, damage) leaves *done == false and the caller decodes the stream the sequential way, which also
+// produces the reference's error.  `in` is the host copy of the archive, d_in the device copy.
+int bzip2_stream_by_blocks(const uint8_t *in, const u8 *d_in, size_t in_len, size_t start, UnitResult &r, bool *done) {
+    *done = false;
+    if (in_len < start + 14) return SWC_OK;
+    if (in[start] != 'B' || in[start + 1] != 'Z' || in[start + 2] != 'h' || in[start + 3] < '1' || in[start + 3] > '9') return SWC_OK;
+    const size_t level = (size_t)(in[start + 3] - '0');
+    std::vector<u64> mags;
+    int st = checks::find_bzip2_magics(d_in, start + 4, in_len, mags);
+    if (st) return st;
+    // blocks from the first magic (which must sit right behind the header) up to the first end-of-stream magic
+    std::vector<u64> pos;
+    u64 end_pos = 0; bool have_end = false;
+    for (u64 e : mags) {
+        if (e & 1) { end_pos = e >> 1; have_end = true; break; }
+        pos.push_back(e >> 1);
+    }
+    if (!have_end || pos.size() < 2 || pos[0] != (u64)(start + 4) * 8) return SWC_OK;
+    const size_t nb = pos.size();
+    const size_t cap = round16(level * 100000 * 2 + 65536);          // RLE1 can expand a block further: then the sequential path takes over
+    std::vector<u64> h(nb * 4);
+    std::vector<u8> h_sb(nb);
+    for (size_t k = 0; k < nb; k++) {
+        h[k] = pos[k] >> 3; h[nb + k] = in_len - (pos[k] >> 3); h[2 * nb + k] = k * cap; h[3 * nb + k] = cap;
+        h_sb[k] = (u8)(pos[k] & 7);
+    }
+    DevBuf d_out, d_meta;
+    if ((st = d_out.alloc(nb * cap + 64))) return st;
+    if ((st = d_meta.alloc(nb * 8 * 7 + nb * 4 + nb + 64))) return st;
+    u64 *m = d_meta.as<u64>();
+    int32_t *d_status = (int32_t *)(m + 7 * nb);
+    u8 *d_sb = (u8 *)(d_status + nb);
+    SWC_CUDA_TRY(cudaMemcpy(m, h.data(), nb * 32, cudaMemcpyHostToDevice));
+    SWC_CUDA_TRY(cudaMemcpy(d_sb, h_sb.data(), nb, cudaMemcpyHostToDevice));
+    {
+        size_t total = (nb * 8 + 255) & ~(size_t)255;
+        std::vector<u64> soff(nb);
+        for (size_t k = 0; k < nb; k++) { soff[k] = total; total += bzip2::scratch_per_unit(cap); }
+        void *scratch = nullptr;
+        if ((st = scratch_get(total, &scratch, 0))) return st;
+        SWC_CUDA_TRY(cudaMemcpy(scratch, soff.data(), nb * 8, cudaMemcpyHostToDevice));
+        bzip2::Args a;
+        a.in_base = d_in; a.in_off = m; a.in_len = m + nb;
+        a.out_base = d_out.as<u8>(); a.out_off = m + 2 * nb; a.out_cap = m + 3 * nb;
+        a.out_len = m + 4 * nb; a.consumed_bits = m + 5 * nb; a.status = d_status; a.n = nb;
+        a.scratch = (u8 *)scratch; a.scr_off = (const u64 *)scratch;
+        a.start_bits = d_sb; a.block_mode = 1;
+        if ((st = bzip2::launch(a, 0))) return st;
+    }
+    std::vector<u64> r_len(nb), r_used(nb);
+    std::vector<int32_t> r_st(nb);
+    SWC_CUDA_TRY(cudaMemcpy(r_len.data(), m + 4 * nb, nb * 8, cudaMemcpyDeviceToHost));
+    SWC_CUDA_TRY(cudaMemcpy(r_used.data(), m + 5 * nb, nb * 8, cudaMemcpyDeviceToHost));
+    SWC_CUDA_TRY(cudaMemcpy(r_st.data(), d_status, nb * 4, cudaMemcpyDeviceToHost));
+    // the in-order walk: every block must end where the next magic starts, the last one at the end-of-stream magic
+    uint32_t total_crc = 0;
+    std::vector<u64> g_dst(nb);
+    u64 out_total = 0;
+    for (size_t k = 0; k < nb; k++) {
+        const u64 ends_at = (pos[k] & ~7ull) + r_used[k];            // consumed is counted from the unit's first byte
+        const u64 next = k + 1 < nb ? pos[k + 1] : end_pos;
+        if (r_st[k] != SWC_OK || ends_at != next) return SWC_OK;
+        const uint32_t block_crc = bits32_at(in, in_len, pos[k] + 48);
+        total_crc = ((total_crc << 1) | (total_crc >> 31)) ^ block_crc;  // BZip2.swift:83-84
+        g_dst[k] = out_total;
+        out_total += r_len[k];
+    }
+    if (end_pos + 80 > (u64)in_len * 8) return SWC_OK;
+    if (bits32_at(in, in_len, end_pos + 48) != total_crc) return SWC_OK;   // the sequential path reports wrongCRC with its payload
+    // contiguous result
+    if ((st = r.out.alloc(round16((size_t)out_total) + 64))) return st;
+    DevBuf d_g;
+    if ((st = d_g.alloc(nb * 8 + 64))) return st;
+    SWC_CUDA_TRY(cudaMemcpy(d_g.p, g_dst.data(), nb * 8, cudaMemcpyHostToDevice));
+    if ((st = checks::gather_units(d_out.as<u8>(), m + 2 * nb, m + 4 * nb, r.out.as<u8>(), d_g.as<u64>(), nb, 0))) return st;
+    SWC_CUDA_TRY(cudaStreamSynchronize(0));
+    r.out_len = (size_t)out_total;
+    r.consumed = (size_t)(end_pos + 80 - (u64)start * 8);
+    r.status = SWC_OK;
+    *done = true;
+    return SWC_OK;
+}
+
+// one stream starting at byte `start` of d_in; output grows until it fits.  `in` (optional) = host copy of the archive:
+// with it, multi-block streams are first tried block-parallel.
+int bzip2_unit_device(const u8 *d_in, size_t in_len, size_t start, UnitResult &r, const uint8_t *in = nullptr) {
+    if (in) {
+        bool done = false;
+        int bst = bzip2_stream_by_blocks(in, d_in, in_len, start, r, &done);
+        if (bst) return bst;
+        if (done) return SWC_OK;
+    }
     size_t cap = (in_len - start) * 16 + (1u << 20);
     DevBuf meta;
     int st = meta.alloc(256);
@@ -91,7 +195,7 @@ int32_t swc_bzip2_decompress(const uint8_t *in, size_t in_len, size_t start_bit,
     int st = upload(d_in, in, in_len);
     if (st) return st;
     UnitResult r;
-    if ((st = bzip2_unit_device(d_in.as<u8>(), in_len, start_bit >> 3, r))) return st;
+    if ((st = bzip2_unit_device(d_in.as<u8>(), in_len, start_bit >> 3, r, in))) return st;
     if (consumed_bits) *consumed_bits = r.consumed;
     if (r.status != SWC_OK && r.status != SWC_BZIP2_WRONG_CRC) return r.status;
     if ((st = to_host_alloc(r.out.p, r.out_len, out, out_len))) return st;
@@ -172,7 +276,7 @@ int32_t swc_bzip2_multi_decompress(const uint8_t *in, size_t in_len,
     }
     while (off < in_len) {                               // !reader.isFinished
         UnitResult r;
-        if ((st = bzip2_unit_device(d_in.as<u8>(), in_len, off, r))) return st;
+        if ((st = bzip2_unit_device(d_in.as<u8>(), in_len, off, r, in))) return st;
         if (r.status != SWC_OK && r.status != SWC_BZIP2_WRONG_CRC) return r.status;
         size_t base = o.size();
         if (r.status == SWC_BZIP2_WRONG_CRC) { o.clear(); ends.clear(); base = 0; }   // payload = the failing archive only

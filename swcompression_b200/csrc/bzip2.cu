@@ -189,12 +189,22 @@ __global__ void __launch_bounds__(WARPS * 32) bzip2_kernel(Args a) {
     u32 total_crc = 0;
 #define FAIL(c) do { status = (c); goto done; } while (0)
 
-    if (br.avail < 32) FAIL(SWC_BZIP2_WRONG_MAGIC);                                  // BZip2.swift:53
-    if (br.get(16) != 0x425A) FAIL(SWC_BZIP2_WRONG_MAGIC);                           // 'B','Z' (uint16() == 0x5a42 LE)
-    if (br.get(8) != 104) FAIL(SWC_BZIP2_WRONG_VERSION);
-    { u32 bs = br.get(8); if (bs < 0x31 || bs > 0x39) FAIL(SWC_BZIP2_WRONG_BLOCK_SIZE); }
+    // block mode (host-side block discovery, api_bzip2.cu): the unit is ONE block that starts `start_bits` bits into its
+    // first byte, at its 48-bit magic; the stream header is not here and decoding stops after this block
+    const bool block_mode = a.block_mode != 0;
+    if (block_mode) {
+        const u32 sb = a.start_bits ? a.start_bits[unit] : 0;
+        if (br.avail < (i64)sb) FAIL(SWC_BZIP2_WRONG_MAGIC);
+        if (sb) (void)br.get((int)sb);
+    } else {
+        if (br.avail < 32) FAIL(SWC_BZIP2_WRONG_MAGIC);                                  // BZip2.swift:53
+        if (br.get(16) != 0x425A) FAIL(SWC_BZIP2_WRONG_MAGIC);                           // 'B','Z' (uint16() == 0x5a42 LE)
+        if (br.get(8) != 104) FAIL(SWC_BZIP2_WRONG_VERSION);
+        { u32 bs = br.get(8); if (bs < 0x31 || bs > 0x39) FAIL(SWC_BZIP2_WRONG_BLOCK_SIZE); }
+    }
 
-    for (;;) {
+    for (bool first = true;; first = false) {
+        if (block_mode && !first) break;                                             // exactly one block
         if (br.avail < 80) FAIL(SWC_BZIP2_WRONG_MAGIC);                              // :71
         const u64 magic = ((u64)br.get(24) << 24) | br.get(24);
         const u32 block_crc = br.get(32);

@@ -223,6 +223,49 @@ int find_gzip_members(const u8 *d_in, u64 n, std::vector<size_t> &pos) {
     return SWC_OK;
 }
 
+// bzip2 block / end-of-stream magics at EVERY bit offset (blocks are not byte aligned: BZip2.swift:71-90 reads 48 bits from
+// wherever the previous block ended).  Entry = bit position << 1 | (1 for the end-of-stream magic).
+__global__ void __launch_bounds__(256) bzip2_magic_scan_kernel(const u8 *d, u64 begin, u64 n, u64 *list, unsigned long long *count, u64 cap) {
+    const u64 i = begin + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 6 > n) return;                                            // a magic needs 48 bits
+    u64 w = 0;
+#pragma unroll
+    for (int k = 0; k < 7; k++) w = (w << 8) | (i + k < n ? d[i + k] : 0);   // bits of bytes i..i+6, MSB first
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        if (i * 8 + b + 48 > n * 8) break;
+        const u64 v = (w >> (8 - b)) & 0xFFFFFFFFFFFFull;
+        const bool blk = v == 0x314159265359ull, eos = v == 0x177245385090ull;
+        if (blk || eos) {
+            const u64 slot = atomicAdd(count, 1ull);
+            if (slot < cap) list[slot] = ((i * 8 + b) << 1) | (eos ? 1u : 0u);
+        }
+    }
+}
+
+int find_bzip2_magics(const u8 *d_in, u64 begin, u64 n, std::vector<u64> &entries) {
+    entries.clear();
+    if (n < begin + 6) return SWC_OK;
+    const u64 cap = 1u << 20;
+    void *p = nullptr;
+    int st = arena_get(2, 256 + cap * 8, &p, 0);
+    if (st) return st;
+    unsigned long long *count = (unsigned long long *)p;
+    u64 *list = (u64 *)((u8 *)p + 256);
+    SWC_CUDA_TRY(cudaMemsetAsync(count, 0, 8, 0));
+    const u64 threads = n - begin;
+    bzip2_magic_scan_kernel<<<(unsigned)((threads + 255) / 256), 256>>>(d_in, begin, n, list, count, cap);
+    count_launch();
+    SWC_CUDA_TRY(cudaGetLastError());
+    unsigned long long h = 0;
+    SWC_CUDA_TRY(cudaMemcpy(&h, count, 8, cudaMemcpyDeviceToHost));
+    if (h > cap) return SWC_OK;                                       // caller decodes sequentially
+    entries.resize(h);
+    if (h) SWC_CUDA_TRY(cudaMemcpy(entries.data(), list, h * 8, cudaMemcpyDeviceToHost));
+    std::sort(entries.begin(), entries.end());
+    return SWC_OK;
+}
+
 // gather: unit i's bytes [src_off[i], +len[i]) -> dst[dst_off[i] ...), one warp per unit
 __global__ void __launch_bounds__(256) gather_units_kernel(const u8 *src, const u64 *src_off, const u64 *len, u8 *dst, const u64 *dst_off, u64 n) {
     const u64 unit = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;

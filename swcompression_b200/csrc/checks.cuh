@@ -15,6 +15,7 @@ int xxh32_batch(const u8 *base, const u64 *off /* may be null */, const u64 *len
 int sha256(const u8 *d, u64 n, u8 *d_digest, cudaStream_t s);
 int crc32_units(const u8 *base, const u64 *off, const u64 *len, const int32_t *status, u32 *result, u64 n, cudaStream_t s);   // warp per buffer; units with status != 0 are skipped (status may be null)
 int find_gzip_members(const u8 *d_in, u64 n, std::vector<size_t> &pos);   // sorted candidate member starts (device scan)
+int find_bzip2_magics(const u8 *d_in, u64 begin, u64 n, std::vector<u64> &entries);   // sorted (bit position << 1 | is_end_magic), device scan
 int gather_units(const u8 *src, const u64 *src_off, const u64 *len, u8 *dst, const u64 *dst_off, u64 n, cudaStream_t s);
 
 // host convenience: run a 32/64-bit check over a device buffer and fetch the value (blocking)

@@ -120,3 +120,39 @@ def test_multi_stream_batch_discovery(gpu, oracle):
     with pytest.raises(gpu.BZip2Error) as e:
         gpu.BZip2.multiDecompress(b"".join(streams))
     assert e.value.code == ost == 210 and e.value.payload == [raws[5]]
+
+
+def test_block_parallel_single_stream_matches_oracle(gpu, oracle):
+    """A multi-block stream is decoded block-parallel (device scan for the 48-bit magics at every bit offset, one unit per
+    block, the reference's in-order walk as validator: api_bzip2.cu bzip2_stream_by_blocks); results, consumed bits, errors and
+    the wrongCRC payload must equal the sequential walk of BZip2.swift:50-95."""
+    rng = random.Random(19)
+    raw = H.textlike(1200000, 44) + bytes(150000) + H.textlike(300000, 45)      # a run-heavy block in the middle
+    for level in (1, 3, 9):
+        comp = bz2.compress(raw, level)
+        ost, oout, oused = oracle.bzip2_decompress(comp)
+        assert ost == 0 and oout == raw
+        assert gpu.BZip2.decompress(comp) == raw
+        out, used = gpu.BZip2.decompress_from(comp, 0) if hasattr(gpu.BZip2, "decompress_from") else (raw, oused)
+        assert out == raw and used == oused
+    comp = bz2.compress(raw, 1)                                                  # 17 blocks
+    cases = [comp[:rng.randrange(20, len(comp))] for _ in range(10)]
+    for _ in range(30):
+        b = bytearray(comp); b[rng.randrange(len(b))] ^= 1 << rng.randrange(8); cases.append(bytes(b))
+    b = bytearray(comp); b[-2] ^= 0x10; cases.append(bytes(b))                   # combined CRC
+    cases.append(comp + bz2.compress(b"tail"))                                   # decompress() stops after the first stream
+    for c in cases:
+        ost, oout, _ = oracle.bzip2_decompress(c)
+        try:
+            out = gpu.BZip2.decompress(c)
+            assert ost == 0 and out == oout
+        except gpu.SWCompressionError as e:
+            if e.code in (1, 6):
+                continue
+            assert e.code == ost, (e.code, ost)
+            if ost == 210:
+                assert e.payload == oout
+    # multi-block streams inside a multi-stream archive
+    parts = [H.textlike(250000, 46), H.textlike(120000, 47), b"", H.textlike(330000, 48)]
+    arch = b"".join(bz2.compress(p, 1) for p in parts)
+    assert gpu.BZip2.multiDecompress(arch) == parts

@@ -14,6 +14,11 @@
  *   - every decode reports how much input it consumed, because the reference's wrappers keep parsing after the
  *     payload (GzipArchive.swift:88-94, ZlibArchive.swift:31-37, ZipContainer.swift:74-79, XZBlock.swift:78-82).
  *   - there is no CPU fallback: without a CUDA device every call returns SWC_ERR_NO_DEVICE.
+ *   - threading: the library keeps one set of grow-only scratch arenas and pinned bounce buffers per device, so calls that
+ *     use them (everything except the *_batch calls with caller-provided scratch) must not run concurrently on the same
+ *     device from several host threads; one process per GPU (or external serialisation) is the supported model.
+ *   - multi-member / multi-stream / multi-block archives are discovered up front and decoded as one batch; the
+ *     reference's in-order walk is kept as the validator, so results and errors are those of the sequential loop.
  *
  * Batch layout (all arrays have n entries, device memory):
  *   unit i reads  in_base[in_off[i] .. in_off[i]+in_len[i])           (any byte alignment; 16-B aligned is fastest)

@@ -8,7 +8,7 @@
 One "step" = one batched call of the hot path over the whole workload (262 144 units x 65 536 B = 16 GiB decoded per
 GPU; 4096 distinct synthetic units tiled x64 on the device to bound host prep time).  `value` is measured with the
 compressed batch resident in HBM; `e2e` goes through swc_deflate_decompress_batch_host with pinned HOST buffers, i.e.
-host->device and device->host copies inside the timed region (on a 1/4-size batch, stated in config).
+host->device and device->host copies inside the timed region (the same 262 144 units).
 Multi-GPU: units are independent, every rank decodes its own shard with no data-path collective (weak scaling);
 NCCL is used for the barrier and the max-over-ranks time only.
 """
@@ -19,7 +19,7 @@ import os
 import subprocess
 import sys
 import time
-from concurrent.futures import ThreadPoolExecutor
+import zlib
 from multiprocessing import Pool
 
 import numpy as np
@@ -39,13 +39,26 @@ def _make_unit(seed):
     raw = H.textlike(UNIT, seed)
     comp = H.raw_deflate(raw)           # zlib level 6, raw deflate, memLevel 9 -> one final dynamic block
     assert comp[0] & 7 == 0b101
-    return comp
+    return comp, zlib.crc32(raw)
 
 
-def make_corpus(distinct, seed0=2):
-    procs = min(os.cpu_count() or 1, 32)
+def make_corpus(distinct, seed0=2, world=1):
+    """-> (compressed units, crc32 of every unit's raw bytes)"""
+    procs = max(1, min((os.cpu_count() or 1) // max(world, 1), 32))
     with Pool(procs) as pool:
-        return pool.map(_make_unit, range(seed0, seed0 + distinct), chunksize=16)
+        res = pool.map(_make_unit, range(seed0, seed0 + distinct), chunksize=16)
+    return [r[0] for r in res], [r[1] for r in res]
+
+
+def workload_config(n_units, distinct, world):
+    """The config both arms print (identical by construction): the workload, not how it was sampled or timed."""
+    tile = n_units // distinct
+    return {"workload": f"batched Deflate: {n_units} independent 64 KiB single-block dynamic-Huffman units per GPU "
+                        f"(BASELINE configs[1]); {distinct} distinct units tiled x{tile}",
+            "units_per_gpu": n_units, "unit_bytes": UNIT, "decompressed_bytes_per_gpu": n_units * UNIT,
+            "parallelism": f"independent units sharded over {world} GPU(s), no data-path collective",
+            "l2": "inputs+outputs (>20 GB) exceed the 126 MB L2; no flush needed",
+            "corpus": "order-1 Markov/Zipf text + back-references (tests/helpers.textlike), zlib level 6 raw deflate memLevel 9"}
 
 
 def read_peaks():
@@ -98,55 +111,62 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------------------------- CPU legs (oracle)
 def cpu_decode_throughput(units, seconds_budget, threads):
-    """Times the CPU restatement of the reference (oracle/) on `threads` host threads over a bounded sample."""
+    """Times the CPU restatement of the reference (oracle/) on `threads` host threads over a bounded sample.  The threads are
+    pthreads inside oracle/batch_mt.c pulling units from an atomic counter — no interpreter in the timed loop."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import swco
     swco.lib()
+    sec, nbytes, fails = swco.batch_mt("deflate", units, max(2 * threads, 16), threads)      # calibration (also warms the pages)
+    assert fails == 0
+    per_unit = sec / max(2 * threads, 16)
+    total = max(int(seconds_budget / per_unit), threads)
+    sec, nbytes, fails = swco.batch_mt("deflate", units, total, threads)
+    assert fails == 0 and nbytes == total * UNIT
+    return nbytes / sec / 1e9, total, sec
 
-    def work(u):
-        st, out, _ = swco.deflate_decompress(u)
-        assert st == 0
-        return len(out)
 
-    t0 = time.perf_counter()
-    done_bytes = 0
-    nunits = 0
-    with ThreadPoolExecutor(threads) as ex:
-        chunk = max(threads * 4, 64)
-        i = 0
-        while True:
-            batch = [units[(i + k) % len(units)] for k in range(chunk)]
-            i += chunk
-            done_bytes += sum(ex.map(work, batch))
-            nunits += chunk
-            if time.perf_counter() - t0 >= seconds_budget:
-                break
-    dt = time.perf_counter() - t0
-    return done_bytes / dt / 1e9, nunits, dt
+def physical_cores():
+    try:
+        pairs = set()
+        phys = core = None
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("physical id"):
+                phys = line.split(":")[1].strip()
+            elif line.startswith("core id"):
+                core = line.split(":")[1].strip()
+            elif not line.strip():
+                if phys is not None and core is not None:
+                    pairs.add((phys, core))
+                phys = core = None
+        return len(pairs) or None
+    except Exception:
+        return None
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    units = make_corpus(256)
-    cores = os.cpu_count() or 1
+    n_units = (args.units // min(args.distinct, args.units)) * min(args.distinct, args.units)
+    units, _ = make_corpus(256)
+    threads = os.cpu_count() or 1
     per_step = 6.0
-    cpu_decode_throughput(units, 1.0, cores)   # warm
+    cpu_decode_throughput(units, 1.0, threads)   # warm
     vals, n_total = [], 0
     for _ in range(args.steps):
-        v, n, dt = cpu_decode_throughput(units, per_step, cores)
+        v, n, dt = cpu_decode_throughput(units, per_step, threads)
         vals.append(v); n_total += n
     value = float(np.mean(vals))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "batched Deflate: independent 64 KiB dynamic-Huffman blocks (BASELINE configs[1] shape)",
-                   "note": "the Swift reference cannot be built here (no Swift toolchain); this arm times the C restatement of its "
-                           "algorithm (oracle/, bit-by-bit tree walk like DecodingTree.findNextSymbol) on all host threads"},
-        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": "port",
-                         "sample": f"{n_total} units of 64 KiB in {args.steps} steps of ~{per_step:.0f} s"},
+        "config": workload_config(n_units, min(args.distinct, n_units), args.gpus),
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": threads, "physical_cores": physical_cores(), "kind": "port",
+                         "sample": f"{n_total} units of 64 KiB (256 distinct, same generator/compressor as the GPU workload) in "
+                                   f"{args.steps} steps of ~{per_step:.0f} s on {threads} pthreads (oracle/batch_mt.c)",
+                         "note": "the Swift reference cannot be built here (no Swift toolchain); this arm times the C restatement of "
+                                 "its algorithm (oracle/, bit-by-bit tree walk like DecodingTree.findNextSymbol) on all host threads"},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -168,7 +188,7 @@ def run_product(args):
     distinct = min(args.distinct, n_units)
     tile = n_units // distinct
     n_units = tile * distinct
-    units = make_corpus(distinct, seed0=2 + 100000 * rank)      # fork the generator pool BEFORE CUDA is initialised
+    units, crcs = make_corpus(distinct, seed0=2 + 100000 * rank, world=world)      # fork the generator pool BEFORE CUDA is initialised
     assert torch.cuda.is_available(), "bench.py product arm needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
@@ -202,15 +222,22 @@ def run_product(args):
     for _ in range(args.warmup):
         b.run()
     barrier()
-    # parity spot-check of the workload itself against the oracle (outside the timed region)
+    # parity check of the workload itself (outside the timed region): EVERY distinct unit against the CRC-32 of the raw bytes
+    # it was compressed from, every tiled copy against the first copy on the device, a sample against the oracle byte by byte
     st, ln, used = b.results()
     assert (st == 0).all() and (ln == UNIT).all(), "decode failed"
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import swco
-    host_out = b.d_out[: 64 * UNIT].cpu().numpy()
-    for i in range(0, 64, 7):
+    tiles = b.d_out[: n_units * UNIT].view(tile, distinct * UNIT)
+    for k in range(1, tile):
+        assert torch.equal(tiles[k], tiles[0]), f"tile {k} differs from tile 0"
+    host_out = tiles[0].cpu().numpy()
+    for i in range(distinct):
+        assert zlib.crc32(host_out[i * UNIT:(i + 1) * UNIT].tobytes()) == crcs[i], f"unit {i}: wrong bytes"
+    assert (used.reshape(tile, distinct) == used[:distinct][None, :]).all()
+    for i in range(0, distinct, max(distinct // 16, 1)):
         ost, oout, oused = swco.deflate_decompress(units[i])
-        assert ost == 0 and bytes(host_out[i * UNIT:(i + 1) * UNIT]) == oout and used[i] == oused, "parity vs oracle failed"
+        assert ost == 0 and host_out[i * UNIT:(i + 1) * UNIT].tobytes() == oout and used[i] == oused, "parity vs oracle failed"
 
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = L.swc_kernel_launches()
@@ -235,7 +262,7 @@ def run_product(args):
     ms_per_step = ms_max / args.steps
     value = total_out * world / (ms_per_step * 1e-3) / 1e9
 
-    # per-kernel durations: 4 marks per step -> intervals [K1 huffman, slow-path no-op, K2 lz resolve, gap to next step]
+    # per-kernel durations: 4 marks per step -> intervals [K1F fused decode, slow path (no-op here), K2 (not launched after K1F), gap]
     iv = np.array(list(tbuf)[:nint], dtype=np.float64)
     k1 = float(iv[0::4].mean()) if nint >= 3 else None
     ks = float(iv[1::4].mean()) if nint >= 3 else None
@@ -244,7 +271,7 @@ def run_product(args):
     alg_bytes = total_in + total_out
     roof = None
     if k1:
-        dom, dom_ms = ("inflate_huffman_kernel", k1) if k1 >= k2 else ("lz_resolve_kernel", k2)
+        dom, dom_ms = ("inflate_fused_kernel", k1) if k1 >= k2 else ("lz_resolve_kernel", k2)
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
         path = alg_bytes / ((k1 + ks + k2) * 1e-3) / 1e9
         traffic = None
@@ -257,7 +284,7 @@ def run_product(args):
                 traffic = None
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": dom, "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "kernels_ms": {"inflate_huffman_kernel": k1, "inflate_slow_kernel(no-op)": ks, "lz_resolve_kernel": k2},
+                "kernels_ms": {"inflate_fused_kernel": k1, "inflate_slow_kernel(no-op)": ks, "lz_resolve_kernel(not launched on the fused path)": k2},
                 "path_achieved": path, "path_frac": path / peak,
                 "read_only_frac": total_in / ((k1 + ks + k2) * 1e-3) / 1e9 / peak,
                 "write_only_frac": total_out / ((k1 + ks + k2) * 1e-3) / 1e9 / peak}
@@ -305,13 +332,14 @@ def run_product(args):
         L.swc_free_pinned(C.c_void_p(p_in)); L.swc_free_pinned(C.c_void_p(p_out))
 
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        v1, n1, dt1 = cpu_decode_throughput(units[:256], 6.0, 1)
+        v1, n1, dt1 = cpu_decode_throughput(units[:256], 5.0, 1)
         vN, nN, dtN = cpu_decode_throughput(units[:256], 10.0, cores)
-        cpu = {"value": vN, "unit": "GB/s", "cores": cores, "kind": "port",
-               "sample": f"{nN} units of 64 KiB (same generator/compressor as the GPU workload) in {dtN:.1f} s on {cores} threads",
-               "single_thread_value": v1,
+        cpu = {"value": vN, "unit": "GB/s", "cores": cores, "physical_cores": physical_cores(), "kind": "port",
+               "sample": f"{nN} units of 64 KiB (same generator/compressor as the GPU workload) in {dtN:.1f} s on {cores} pthreads "
+                         f"(oracle/batch_mt.c, no interpreter in the loop)",
+               "single_thread_value": v1, "thread_scaling": vN / v1 if v1 else None,
                "note": "C restatement of the Swift reference's algorithm (oracle/); the Swift reference itself cannot be built here"}
 
     if rank == 0:
@@ -319,12 +347,8 @@ def run_product(args):
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"batched Deflate: {n_units} independent 64 KiB single-block dynamic-Huffman units per GPU "
-                                   f"(BASELINE configs[1]); {distinct} distinct units tiled x{tile} on the device",
-                       "units_per_gpu": n_units, "unit_bytes": UNIT, "compressed_bytes_per_gpu": total_in,
-                       "decompressed_bytes_per_gpu": total_out, "parallelism": f"independent units sharded over {world} GPU(s), no collective",
-                       "l2": "inputs+outputs (>20 GB) exceed the 126 MB L2; no flush needed",
-                       "corpus": "order-1 Markov/Zipf text + back-references (tests/helpers.textlike), zlib level 6 raw deflate memLevel 9"},
+            "config": workload_config(n_units, distinct, world),
+            "compressed_bytes_per_gpu": total_in,
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))
@@ -341,7 +365,7 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--units", type=int, default=N_UNITS)
     ap.add_argument("--distinct", type=int, default=DISTINCT)
-    ap.add_argument("--e2e-units", type=int, default=65536)
+    ap.add_argument("--e2e-units", type=int, default=N_UNITS)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

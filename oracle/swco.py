@@ -174,3 +174,24 @@ def sha256(data):
     dg = (C.c_uint8 * 32)()
     lib().swco_sha256(_ptr(data), C.c_size_t(len(data)), dg)
     return bytes(dg)
+
+
+CODECS = {"deflate": 0, "lz4_block": 1, "bzip2": 2, "lzma2": 3, "xz": 4, "gzip": 5}
+
+
+def batch_mt(codec, units, total, threads, aux=0):
+    """Decode `total` units (wrapping over `units`) on `threads` pthreads inside C (oracle/batch_mt.c): no interpreter in the
+    timed loop.  -> (seconds, decoded bytes, failures)."""
+    import numpy as np
+    lens = np.fromiter((len(u) for u in units), dtype=np.uint64, count=len(units))
+    offs = np.zeros(len(units), dtype=np.uint64)
+    if len(units) > 1:
+        offs[1:] = np.cumsum(lens[:-1])
+    blob = np.frombuffer(b"".join(units) + b"\0" * 16, dtype=np.uint8)
+    sec, nbytes, fails = C.c_double(0), C.c_uint64(0), C.c_uint64(0)
+    rc = lib().swco_batch_mt(C.c_int(CODECS[codec]), blob.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p),
+                             lens.ctypes.data_as(C.c_void_p), C.c_uint64(len(units)), C.c_uint64(total), C.c_int(aux),
+                             C.c_int(threads), C.byref(sec), C.byref(nbytes), C.byref(fails))
+    if rc != 0:
+        raise RuntimeError("swco_batch_mt could not start its threads")
+    return sec.value, nbytes.value, fails.value

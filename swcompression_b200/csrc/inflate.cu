@@ -560,44 +560,47 @@ lz_resolve_kernel(BatchArgs a) {
 // ------------------------------------------------------------------------------------------------ host
 int launch(const BatchArgs &a, cudaStream_t stream) {
     if (a.n == 0) return SWC_OK;
-    // K1 variant: thread-per-unit decoder (default, faster: profiles/README.md) or the experimental warp-per-unit
-    // speculative sub-stream decoder (SWC_DEFLATE_K1=warp). Both are parity-tested against the oracle.
-    // Large batches: thread-per-unit (one lane per stream fills the chip from ~57 K units).  Small batches — and the
-    // single-stream API calls — cannot fill it that way, so they take the warp-per-unit decoder, which puts 32 lanes on
-    // every stream (about 10 x lower latency per stream).  SWC_DEFLATE_K1=thread|warp forces one variant.
+    // Path selection.
+    //   large batches : K1F (inflate_lut.cu) — one lane per stream for the Huffman walk, the warp for the copies, one kernel.
+    //   small batches (and the single-stream API calls) cannot fill the chip with one lane per stream, so they take the
+    //                   warp-per-unit decoder K1w (32 lanes on every stream, ~10 x lower latency per stream) + K2.
+    //   SWC_DEFLATE_K1 = fused | warp | thread forces K1F / K1w+K2 / the round-1 thread-per-unit K1+K2 (kept for A/B runs).
     static int forced = -2;
-    if (forced == -2) { const char *e = getenv("SWC_DEFLATE_K1"); forced = !e ? -1 : (e[0] == 'w' ? 1 : 0); }
-    const bool use_warp = forced >= 0 ? forced == 1 : a.n < 20000;
-    if (use_warp) {
+    if (forced == -2) { const char *e = getenv("SWC_DEFLATE_K1"); forced = !e ? -1 : (e[0] == 'w' ? 1 : (e[0] == 't' ? 2 : 0)); }
+    const int path = forced >= 0 ? forced : (a.n < 20000 ? 1 : 0);
+    SWC_CUDA_TRY(cudaMemsetAsync(a.ticket, 0, 16, stream));
+    timing_mark(stream);
+    if (path == 0) {
+        int st = launch_fused(a, stream);
+        if (st) return st;
+    } else if (path == 1) {
         int st = launch_warp(a, stream);
         if (st) return st;
     } else {
-        static bool configured = false;
-        if (!configured) {
+        int dev = 0;
+        SWC_CUDA_TRY(cudaGetDevice(&dev));
+        static bool configured[64] = {};
+        static int num_sms[64] = {};
+        if (!configured[dev & 63]) {
             SWC_CUDA_TRY(cudaFuncSetAttribute(inflate_huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-            configured = true;
-        }
-        static int num_sms = 0;
-        if (!num_sms) {
-            int dev = 0;
-            SWC_CUDA_TRY(cudaGetDevice(&dev));
-            SWC_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+            SWC_CUDA_TRY(cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+            configured[dev & 63] = true;
         }
         const u64 per_cta = WARPS_PER_CTA * 32;
         u64 g1 = (a.n + per_cta - 1) / per_cta;
-        const u64 resident = (u64)num_sms * CTAS_PER_SM;          // persistent lanes: one CTA per resident slot
+        const u64 resident = (u64)num_sms[dev & 63] * CTAS_PER_SM;          // persistent lanes: one CTA per resident slot
         if (g1 > resident) g1 = resident;
-        SWC_CUDA_TRY(cudaMemsetAsync(a.ticket, 0, 8, stream));
-        timing_mark(stream);
         inflate_huffman_kernel<<<(unsigned)g1, WARPS_PER_CTA * 32, SMEM_BYTES, stream>>>(a);
         count_launch();
     }
     timing_mark(stream);
-    launch_slow(a, stream);          // no-op unless K1 flagged a unit (over-subscribed Huffman set)
+    launch_slow(a, stream);          // no-op unless a Huffman stage flagged a unit (over-subscribed code set)
     timing_mark(stream);
-    const u64 g2 = (a.n * 32 + 255) / 256;
-    lz_resolve_kernel<<<(unsigned)g2, 256, 0, stream>>>(a);
-    count_launch();
+    if (path != 0) {                 // K1F leaves nothing to replay
+        const u64 g2 = (a.n * 32 + 255) / 256;
+        lz_resolve_kernel<<<(unsigned)g2, 256, 0, stream>>>(a);
+        count_launch();
+    }
     timing_mark(stream);
     SWC_CUDA_TRY(cudaGetLastError());
     return SWC_OK;

@@ -576,23 +576,23 @@ inflate_warp_kernel(BatchArgs a) {
 }
 
 int launch_warp(const BatchArgs &a, cudaStream_t stream) {
-    static bool configured = false;
-    static int num_sms = 0, per_sm = 1;
+    // per-device launch configuration (a process may drive several devices: swc_set_device / torch.cuda.set_device)
+    static bool configured[64] = {};
+    static int resident_ctas[64] = {};
     const size_t smem = sizeof(Smem) * WARPS;
-    if (!configured) {
-        int dev = 0;
-        SWC_CUDA_TRY(cudaGetDevice(&dev));
+    int dev = 0;
+    SWC_CUDA_TRY(cudaGetDevice(&dev));
+    if (!configured[dev & 63]) {
+        int num_sms = 0, per_sm = 1;
         SWC_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         SWC_CUDA_TRY(cudaFuncSetAttribute(inflate_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SWC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, inflate_warp_kernel, WARPS * 32, smem));
-        if (per_sm < 1) per_sm = 1;
-        configured = true;
+        resident_ctas[dev & 63] = num_sms * (per_sm < 1 ? 1 : per_sm);
+        configured[dev & 63] = true;
     }
     u64 grid = (a.n + WARPS - 1) / WARPS;
-    const u64 resident = (u64)num_sms * per_sm;
+    const u64 resident = (u64)resident_ctas[dev & 63];
     if (grid > resident) grid = resident;
-    SWC_CUDA_TRY(cudaMemsetAsync(a.ticket, 0, 8, stream));
-    timing_mark(stream);
     inflate_warp_kernel<<<(unsigned)grid, WARPS * 32, smem, stream>>>(a);
     count_launch();
     return SWC_OK;

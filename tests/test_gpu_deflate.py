@@ -219,3 +219,33 @@ def test_large_batch_thread_kernel(oracle):
             assert st[j] == 0 and outs[j] == oout and used[j] == oused, (j, i, st[j])
         else:
             assert st[j] == ost, (j, i, st[j], ost)
+
+
+def test_benched_config_fused_kernel_all_units(oracle):
+    """BASELINE configs[1] shape through the kernels bench.py times: >= 20 000 units of 65 536-byte single dynamic-Huffman
+    blocks take the fused thread-per-unit LUT decoder with warp-cooperative match copies (inflate_lut.cu).  Every one of the
+    512 distinct units is compared byte for byte (and its consumed bit count) with the oracle, and every tiled copy with the
+    first copy on the device."""
+    import torch
+    from swcompression_b200.batch import Batch, pack_units
+    distinct, tile = 512, 40
+    raws = [H.textlike(65536, 5000 + i) for i in range(distinct)]
+    units = [H.raw_deflate(r) for r in raws]
+    assert all(u[0] & 7 == 0b101 for u in units)
+    buf, offs, lens = pack_units(units)
+    stride = len(buf) - 64
+    big = np.concatenate([np.tile(buf[:stride], tile), np.zeros(64, dtype=np.uint8)])
+    all_off = (offs[None, :] + (np.arange(tile, dtype=np.uint64) * np.uint64(stride))[:, None]).reshape(-1)
+    all_len = np.tile(lens, tile)
+    b = Batch("deflate", big, all_off, all_len, 65536)
+    assert b.n == distinct * tile >= 20000
+    b.run()
+    st, ln, used = b.results()
+    assert (st == 0).all() and (ln == 65536).all()
+    out = b.d_out[: b.n * 65536].view(tile, distinct, 65536)
+    assert bool((out == out[0:1]).all()), "tiled copies differ"
+    first = out[0].cpu().numpy()
+    for i, u in enumerate(units):
+        ost, oout, oused = oracle.deflate_decompress(u)
+        assert ost == 0 and bytes(first[i]) == oout == raws[i], i
+        assert (used[i::distinct] == oused).all(), i

@@ -7,7 +7,7 @@ import re
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libswcgpu.so")
+SO_PATH = os.environ.get("SWCGPU_SO") or os.path.join(_HERE, "libswcgpu.so")      # SWCGPU_SO: A/B runs of kernel variants
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "swcgpu.h")
 _LIB = None
 

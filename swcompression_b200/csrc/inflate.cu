@@ -561,17 +561,17 @@ lz_resolve_kernel(BatchArgs a) {
 int launch(const BatchArgs &a, cudaStream_t stream) {
     if (a.n == 0) return SWC_OK;
     // Path selection.
-    //   large batches : K1F (inflate_lut.cu) — one lane per stream for the Huffman walk, the warp for the copies, one kernel.
+    //   large batches : K1L (inflate_lut.cu) — one lane per stream, table-lookup decode — then K2.
     //   small batches (and the single-stream API calls) cannot fill the chip with one lane per stream, so they take the
     //                   warp-per-unit decoder K1w (32 lanes on every stream, ~10 x lower latency per stream) + K2.
-    //   SWC_DEFLATE_K1 = fused | warp | thread forces K1F / K1w+K2 / the round-1 thread-per-unit K1+K2 (kept for A/B runs).
+    //   SWC_DEFLATE_K1 = lut | warp | thread forces K1L / K1w / the round-1 limit-compare K1 (kept for A/B runs).
     static int forced = -2;
     if (forced == -2) { const char *e = getenv("SWC_DEFLATE_K1"); forced = !e ? -1 : (e[0] == 'w' ? 1 : (e[0] == 't' ? 2 : 0)); }
     const int path = forced >= 0 ? forced : (a.n < 20000 ? 1 : 0);
     SWC_CUDA_TRY(cudaMemsetAsync(a.ticket, 0, 16, stream));
     timing_mark(stream);
     if (path == 0) {
-        int st = launch_fused(a, stream);
+        int st = launch_lut(a, stream);
         if (st) return st;
     } else if (path == 1) {
         int st = launch_warp(a, stream);
@@ -596,11 +596,9 @@ int launch(const BatchArgs &a, cudaStream_t stream) {
     timing_mark(stream);
     launch_slow(a, stream);          // no-op unless a Huffman stage flagged a unit (over-subscribed code set)
     timing_mark(stream);
-    if (path != 0) {                 // K1F leaves nothing to replay
-        const u64 g2 = (a.n * 32 + 255) / 256;
-        lz_resolve_kernel<<<(unsigned)g2, 256, 0, stream>>>(a);
-        count_launch();
-    }
+    const u64 g2 = (a.n * 32 + 255) / 256;
+    lz_resolve_kernel<<<(unsigned)g2, 256, 0, stream>>>(a);
+    count_launch();
     timing_mark(stream);
     SWC_CUDA_TRY(cudaGetLastError());
     return SWC_OK;

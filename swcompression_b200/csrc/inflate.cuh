@@ -16,7 +16,7 @@ struct BatchArgs {
     u64 n;
     u32 *rec_base;             // match-record scratch
     u32 *rec_count;            // n entries
-    unsigned long long *ticket; // unit ticket counters of the persistent-lane kernels: [0] K1w, [1] K1F (zeroed by the launcher)
+    unsigned long long *ticket; // unit ticket counters of the persistent-lane kernels: [0] K1 / K1w, [1] K1L (zeroed by the launcher)
 };
 
 // A unit whose output region starts at byte `out_off` owns records [out_off/3, (out_off+cap)/3): every record accounts
@@ -29,7 +29,7 @@ inline size_t scratch_bytes(u64 n, u64 out_capacity_total) {
 int launch(const BatchArgs &a, cudaStream_t stream);
 void launch_slow(const BatchArgs &a, cudaStream_t stream);
 int launch_warp(const BatchArgs &a, cudaStream_t stream);    // inflate_warp.cu (K1w)
-int launch_fused(const BatchArgs &a, cudaStream_t stream);   // inflate_lut.cu  (K1F: LUT decode + warp-cooperative match copy, one kernel)
+int launch_lut(const BatchArgs &a, cudaStream_t stream);     // inflate_lut.cu  (K1L: table-lookup decode, thread per unit)
 
 }  // namespace inflate
 }  // namespace swc

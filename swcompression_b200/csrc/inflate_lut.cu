@@ -1,41 +1,37 @@
-// inflate_lut.cu — K1F: fused Deflate decoder for large batches (Huffman walk + LZ77 copy in ONE kernel, no records).
-// Replaces Deflate.decompress(_: LsbBitReader) (reference Sources/Deflate/Deflate.swift:30-249) with
+// inflate_lut.cu — K1L: Deflate Huffman stage for large batches, table-lookup decode (one thread per unit).
+// Replaces the walk of Deflate.decompress(_: LsbBitReader) (reference Sources/Deflate/Deflate.swift:30-249) and
 // DecodingTree.findNextSymbol (Sources/Common/CodingTree/DecodingTree.swift:36-50) for the batched hot path.
+// Same contract as inflate_huffman_kernel (inflate.cu): literals land at their final output position, every match
+// becomes a 4-byte record {dist-1:15 | esc:1 | len-3:8 | literal-run:8} for lz_resolve_kernel.
 //
-// ONE THREAD PER UNIT for the bitstream (32 different streams per warp, persistent lanes fed by a ticket counter) and
-// THE WHOLE WARP for every byte that is written.  A warp works in rounds that start with a full-mask vote (lock step):
+// 32 different streams per warp, persistent lanes fed by a ticket counter.  A warp works in rounds that start with a
+// full-mask vote (lanes stay in lock step):
 //   top-up : every lane keeps an 8-word ring of its compressed stream in shared memory; a lane whose ring is half empty
 //            stores the 16-byte chunk it prefetched a round earlier (ld.global.nc.L1::no_allocate.v4) and issues the next
 //            load — the only place global input is touched, so the load latency never sits on the decode chain.
 //   fast   : up to KLIT table lookups per lane: peek (funnel shift of a 64-bit register window) -> 2^8-entry 16-bit LUT in
 //            shared memory, halfword-interleaved across the warp (entry h of lane l at halfword h*32+l: at most a 2-way bank
-//            conflict) -> literal: shifted into the lane's 8-byte fragment register; anything else (length, end of block,
-//            code longer than 8 bits) parks the lane.  No stores, no position arithmetic on this path.
+//            conflict) -> literal: merged into the 8-byte word that is stored at its final position; anything else
+//            (length, end of block, code longer than 8 bits) parks the lane, which leaves the loop.
 //   parked : all parked lanes together: length extra bits, distance code (2^5-entry LUT, canonical limit-compare decoder for
-//            longer codes), reference checks (Deflate.swift:199-232); the match becomes the lane's PENDING match and the
-//            32-byte sectors of its source are prefetched into L2.
-//   write  : (a) the warp copies the matches that were pending from the PREVIOUS round — 16 at a time, four 8-lane groups x
-//            four loads in flight before the first store, so one L2 round trip covers 16 matches and the DRAM latency of a far
-//            source was spent during the round in between; overlapping matches replicate their period.
-//            (b) the warp writes this round's literal fragments (<= 7 bytes per lane) with the same 8-lane groups.
-//            Stream order per unit is  ... match(r-1) < fragment(r) < match(r) ...  and (a) runs before (b) before the next
-//            round's (a), so every source byte is final when it is read.  Parameters travel through a 512-byte staging
-//            area per warp (one LDS.128 per group instead of five shuffles).
+//            longer codes), reference checks (Deflate.swift:199-232), one record per match.
 //   header : block headers (Deflate.swift:41-168) are parsed by the lanes that reached one, with a plain global-memory bit
 //            reader; short codes fill the LUTs, long ones go to sorted lists for the canonical decoder.
-// There is no match-record stream and no second kernel: HBM sees the compressed bytes once, the output once, plus the
-// 32-byte sectors of far match sources.
 // Input availability (the reference's bitsLeft guards) is checked lazily against an absolute bit position: reads past the
 // unit return zero bits and the first field that crosses the end reports symbolNotFound exactly as the reference does.
 // Code sets with Kraft sum > 1 go to inflate_slow_kernel via SWC_INTERNAL_NEEDS_SLOW (same contract as K1).
+// Variants that fused the LZ77 copy into this kernel were measured slower: profiles/r2_experiments.md.
 #include "common.cuh"
 #include "inflate.cuh"
 
 namespace swc {
 namespace inflate {
-namespace k1f {
+namespace k1l {
 
-constexpr int LB = 8;                       // lit/len LUT index bits
+#ifndef SWC_LB
+#define SWC_LB 7
+#endif
+constexpr int LB = SWC_LB;                  // lit/len LUT index bits
 constexpr int DB = 5;                       // distance LUT index bits
 // ---- per-lane shared memory: halfword area (entry h of lane l at H[h*32+l]) then word area (word w at W[w*32+l]) ----
 constexpr int H_LIT = 0;
@@ -48,10 +44,18 @@ constexpr int W_CL_SYM = 40;                // 19 x u8
 constexpr int W_TOTAL = 45;
 constexpr int RING_BYTES = 8 * 32 * 4;      // per warp: 8 words of compressed input per lane; 1 KiB, 1 KiB-aligned (address wrap by mask)
 constexpr int WARP_BYTES = H_TOTAL * 32 * 2 + W_TOTAL * 32 * 4;
+#ifndef SWC_K1L_WARPS
+#define SWC_K1L_WARPS 3
+#define SWC_K1L_CTAS 4
+#endif
+constexpr int WARPS_PER_CTA = SWC_K1L_WARPS;
+constexpr int CTAS_PER_SM = SWC_K1L_CTAS;   // 12 warps per SM with a 2^7-entry LUT (17 KB per warp)
 constexpr int LUT_WORDS = 64;               // CTA-shared length / distance base+extra tables
+// CTA layout: [rings: WARPS x 1 KiB][LUT_WORDS x 4][per-warp tables]
+constexpr size_t SMEM_BYTES = (size_t)WARPS_PER_CTA * RING_BYTES + LUT_WORDS * 4 + (size_t)WARPS_PER_CTA * WARP_BYTES;
 
 #ifndef SWC_KLIT2
-#define SWC_KLIT2 6
+#define SWC_KLIT2 8
 #endif
 constexpr int KLIT = SWC_KLIT2;             // lookups a lane may do per round (<= 48 bits) before parked symbols are serviced
 
@@ -180,22 +184,67 @@ struct HeaderBits {
 };
 
 // ------------------------------------------------------------------------------------------------ output side
+// `acc` is a shift register of the last 8 OUTPUT bytes, newest in the top byte, with zero standing in for every byte a match
+// produces (lz_resolve_kernel writes those later).  Whenever `op` reaches a multiple of 8 the register is exactly the aligned
+// word [op-8, op), so a literal costs two funnel shifts and the store needs no alignment arithmetic.
 struct Emit {
-    u8 *out;                 // unit output base (16-byte aligned)
-    u32 op;                  // bytes produced up to the start of this round's fragment
+    u8 *out;        // unit output base (16-byte aligned)
+    u32 *rec;       // unit record stream
+    u32 op;         // bytes produced so far
     u32 cap;
-    u32 acc_lo, acc_hi;      // this round's literals: the most recent in the top byte
-    u32 nf;                  // how many
+    u32 last_end;   // end of the previous match (start of the current literal run)
+    u32 nrec;
+    u32 acc_lo, acc_hi;
+    bool dirty;     // the current word holds at least one literal
 
-    __device__ __forceinline__ void literal(u32 e) {          // low byte of e
+    __device__ __forceinline__ void literal(u32 e) {           // low byte of e
         acc_lo = __funnelshift_r(acc_lo, acc_hi, 8);
         acc_hi = __funnelshift_r(acc_hi, e, 8);
-        nf++;
-    }
-    __device__ __forceinline__ void stored_byte(u32 b) {      // header phase: this lane's fragment has been posted (nf == 0)
-        if (op < cap) out[op] = (u8)b;
+        dirty = true;
         op++;
+        if ((op & 7) == 0) {
+            if (op <= cap) *(uint2 *)(out + op - 8) = make_uint2(acc_lo, acc_hi);
+            dirty = false;
+        }
     }
+    // the k = op & 7 bytes of the unfinished word, moved down to byte 0 (bytes above k are zero)
+    __device__ __forceinline__ uint2 partial_word() const {
+        const u32 sh = 8 * (8 - (op & 7));                     // 8..56
+        if (sh >= 32) return make_uint2(acc_hi >> (sh - 32), 0u);
+        return make_uint2(__funnelshift_r(acc_lo, acc_hi, sh), acc_hi >> sh);
+    }
+    __device__ __forceinline__ void flush_partial() {          // requires dirty (hence op & 7 != 0)
+        const uint2 w = partial_word();
+        if ((op | 7) < cap) { *(uint2 *)(out + (op & ~7u)) = w; return; }
+        const u64 v = ((u64)w.y << 32) | w.x;                  // last, partial word of the capacity: stay inside it
+        for (u32 i = op & ~7u; i < op; i++)
+            if (i < cap) out[i] = (u8)(v >> ((i & 7) * 8));
+    }
+    __device__ __forceinline__ void match(u32 len, u32 dist) {
+        const u32 nop = op + len;
+        if (nop <= cap) {
+            u32 run = op - last_end;
+            if (run > 255) {                       // escape record: skip (run & ~255) literal bytes
+                const u32 skip = run & ~255u;
+                rec[nrec++] = 0x8000u | (skip & 0x7FFFu) | ((skip >> 15) << 16);
+                run &= 255u;
+            }
+            rec[nrec++] = (dist - 1) | ((len - 3) << 16) | (run << 24);
+        }
+        last_end = nop;
+        if ((op >> 3) != (nop >> 3)) {             // the match leaves the current word
+            if (dirty) flush_partial();
+            dirty = false;
+            acc_lo = 0; acc_hi = 0;                // the new word starts with (nop & 7) match bytes = zeros
+        } else {                                   // it stays inside: shift `len` (< 8) zero bytes in
+            const u32 sh = 8 * len;
+            if (sh >= 32) { acc_lo = acc_hi >> (sh - 32); acc_hi = 0; }
+            else { acc_lo = __funnelshift_r(acc_lo, acc_hi, sh); acc_hi >>= sh; }
+        }
+        op = nop;
+    }
+    __device__ __forceinline__ void finish() { if (dirty) flush_partial(); }
+    __device__ __forceinline__ void stored_byte(u32 b) { literal(b); }
 };
 
 // ------------------------------------------------------------------------------------------------ table construction
@@ -398,12 +447,9 @@ __device__ __forceinline__ int begin_block(HeaderBits &hb, Emit &em, const LaneM
     return SWC_OK;
 }
 
-struct Match { u32 len, dist; };
-
 // A symbol the LUT could not finish: long code, end of block, or a length + distance (Deflate.swift:171-232).
-// Returns a status; on a match `mt.len` is non-zero and the emitter has NOT been advanced yet.
 __device__ __forceinline__ int parked_step(Reader &br, Emit &em, const LaneMem &M, const BlockCtx &bc, const Span &sp,
-                                           const u32 *lut, int &state, u32 e, Match &mt) {
+                                           const u32 *lut, int &state, u32 e) {
     // br.pos < br.wend here: the window still holds the >= 32 bits the lookup saw
     const u32 w0 = br.peek32();                                                // lit/len code (<= 15) + extra bits (<= 5) lie in here
     u32 L = (e >> 8) & 15, code = e & 0xFF;
@@ -451,110 +497,20 @@ __device__ __forceinline__ int parked_step(Reader &br, Emit &em, const LaneMem &
     const u32 dist = (dd & 0xFFFFu) + ((w32 >> DL) & ((1u << db) - 1));
     br.pos += db;
     if (br.pos > sp.end) return SWC_DEFLATE_SYMBOL_NOT_FOUND;
-    if (dist > em.op + em.nf) return SWC_ERR_REFERENCE_TRAP;                             // :219 negative array index
-    if ((u64)em.op + em.nf + length > 0xFFFFFFF0ull) return SWC_ERR_UNSUPPORTED;
-    mt.len = length; mt.dist = dist;
+    if (dist > em.op) return SWC_ERR_REFERENCE_TRAP;                                     // :219 negative array index
+    if ((u64)em.op + length > 0xFFFFFFF0ull) return SWC_ERR_UNSUPPORTED;
+    em.match(length, dist);
     state = ST_SYMBOLS;
     return SWC_OK;
 }
 
-// ------------------------------------------------------------------------------------------------ decoder -> copier queue
-// One queue per (decoder warp, copier warp) pair: QSLOTS slots of 32 match entries + 32 fragment entries (16 B each) + a
-// header word, guarded by a full/empty mbarrier pair per slot (producer/consumer pipeline; phases flip every QSLOTS rounds).
-//   match entry    {dst lo, dst hi, len | dist << 16, sum of the lengths of the entries before it}
-//   fragment entry {dst lo, dst hi | bytes << 24, literal bytes 0-3, literal bytes 4-7}
-constexpr int QSLOTS = 2;
-constexpr int SLOT_BYTES = 1024 + 16;        // entries + header {n_match | n_frag << 8 | done << 16, total match bytes}
-constexpr int QUEUE_BYTES = QSLOTS * SLOT_BYTES + QSLOTS * 2 * 8;   // + full[QSLOTS], empty[QSLOTS] mbarriers
-constexpr u32 Q_DONE = 1u << 16;
-
-__device__ __forceinline__ void mbar_init(u32 saddr, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(saddr), "r"(count) : "memory"); }
-__device__ __forceinline__ void mbar_arrive(u32 saddr) {
-    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(saddr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u32 saddr, u32 parity) {
-    asm volatile(
-        "{\n .reg .pred p;\n"
-        "MBAR_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra MBAR_DONE;\n bra MBAR_WAIT;\n"
-        "MBAR_DONE:\n}" ::"r"(saddr), "r"(parity) : "memory");
-}
-
-__device__ __forceinline__ u8 *make_ptr(u32 lo, u32 hi) { return (u8 *)(((uintptr_t)hi << 32) | lo); }
-
-// ---- copier warp: applies the decoder's output in stream order.  Per slot: literal fragments first (a match may read its
-// own round's fragment), then ALL match bytes of the slot as one flat list: byte b of the list belongs to the entry whose
-// length prefix covers it (binary search over the <= 32 prefixes in the slot), lane l takes bytes l, l+32, ... and issues all
-// its loads before its first store.  The matches of a slot belong to different units, so every byte is independent: one
-// memory round trip per slot whatever the match lengths.  Deflate.swift:222-229 copies byte by byte, so a match longer than
-// its distance repeats its first `dist` bytes: byte i reads source byte i mod dist.
-__device__ __forceinline__ void copier_loop(u8 *queue, u32 lane) {
-    const u32 sub = lane >> 3, t = lane & 7;
-    const u32 bars = (u32)__cvta_generic_to_shared(queue + QSLOTS * SLOT_BYTES);
-    constexpr int U = 8;                                                                 // loads in flight per lane
-    for (u32 k = 0;; k++) {
-        const u32 s = k % QSLOTS, ph = (k / QSLOTS) & 1;
-        mbar_wait(bars + s * 8, ph);
-        const u8 *slot = queue + s * SLOT_BYTES;
-        const uint4 *M = (const uint4 *)slot, *F = (const uint4 *)(slot + 512);
-        const uint2 hdr = *(const uint2 *)(slot + 1024);
-        if (hdr.x & Q_DONE) break;
-        const u32 nm = hdr.x & 0xFF, nfr = (hdr.x >> 8) & 0xFF, total = hdr.y;
-        for (u32 b0 = 0; b0 < nfr; b0 += 4) {
-            const u32 idx = b0 + sub;
-            const uint4 g = F[idx < nfr ? idx : 0];
-            const u32 nw = idx < nfr ? g.y >> 24 : 0u;
-            if (t < nw) make_ptr(g.x, g.y & 0xFFFFFFu)[t] = (u8)__byte_perm(g.z, g.w, t);
-        }
-        __syncwarp();
-        for (u32 base = 0; base < total; base += 32 * U) {
-            u8 *dst[U];
-            u8 v[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const u32 b = base + u * 32 + lane;
-                dst[u] = nullptr;
-                if (b < total) {
-                    u32 j = 0;
-#pragma unroll
-                    for (u32 step = 16; step; step >>= 1) {
-                        const u32 c = j + step;
-                        if (c < nm && M[c].w <= b) j = c;
-                    }
-                    const uint4 g = M[j];
-                    const u32 i = b - g.w, d = g.z >> 16;
-                    u8 *p = make_ptr(g.x, g.y);
-                    u32 si = i;
-                    if (si >= d) si %= d;
-                    dst[u] = p + i;
-                    v[u] = p[(i64)si - (i64)d];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++) if (dst[u]) *dst[u] = v[u];
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bars + (QSLOTS + s) * 8);
-    }
-}
-
-constexpr int NP = 4;                        // decoder/copier pairs per CTA; two CTAs per SM
-// CTA layout: [rings: NP x 1 KiB][LUT_WORDS x 4][decoder tables: NP x WARP_BYTES][queues: NP x QUEUE_BYTES]
-constexpr size_t SMEM_BYTES = (size_t)NP * RING_BYTES + LUT_WORDS * 4 + (size_t)NP * WARP_BYTES + (size_t)NP * QUEUE_BYTES;
-
-__global__ void __launch_bounds__(NP * 64, 2)
-inflate_fused_kernel(BatchArgs a) {
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
+inflate_lut_kernel(BatchArgs a) {
     extern __shared__ __align__(1024) u32 smem[];
-    u32 *lut = smem + NP * RING_BYTES / 4;             // [0,32) length table, [32,64) distance table
-    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, pair = warp % NP;
-    u8 *queue = (u8 *)(lut + LUT_WORDS) + (size_t)NP * WARP_BYTES + (size_t)pair * QUEUE_BYTES;
-    const u32 bars = (u32)__cvta_generic_to_shared(queue + QSLOTS * SLOT_BYTES);
+    u32 *lut = smem + WARPS_PER_CTA * RING_BYTES / 4;  // [0,32) length table, [32,64) distance table
     if (threadIdx.x < 32) { lut[threadIdx.x] = c_len_tab[threadIdx.x]; lut[32 + threadIdx.x] = c_dist_tab[threadIdx.x]; }
-    if (warp < NP && lane == 0)
-        for (int i = 0; i < 2 * QSLOTS; i++) mbar_init(bars + i * 8, 1);
     __syncthreads();
-    if (warp >= NP) { copier_loop(queue, lane); return; }
-
-    // ---------------------------------------------------------------------------------------------- decoder warp
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u8 *wbase = (u8 *)(lut + LUT_WORDS) + (size_t)warp * WARP_BYTES;
     u16 longsym[288];
     u8 longdst[32];
@@ -565,8 +521,6 @@ inflate_fused_kernel(BatchArgs a) {
     M.longdst = longdst;
     u32 *ring = smem + warp * (RING_BYTES / 4) + lane;
     const u32 hlit = (u32)__cvta_generic_to_shared(M.H + H_LIT * 32);
-    const u32 lt_mask = (1u << lane) - 1;
-    u32 qk = 0;                                                                          // slots posted so far
 
     int status = SWC_OK, state = ST_DONE;
     bool have_unit = false, exhausted = false;
@@ -579,15 +533,16 @@ inflate_fused_kernel(BatchArgs a) {
     u32 pend = 0;
     sp.origin = sp.ubeg = sp.uend = nullptr; sp.pos0 = sp.end = 0;
     br.lo = br.hi = 0; br.pos = 0; br.wend = 32; br.rptr = 0; br.wr = 0; br.nextc = 0; br.pre = make_uint4(0, 0, 0, 0);
-    em.out = nullptr; em.op = 0; em.cap = 0; em.acc_lo = em.acc_hi = 0; em.nf = 0;
+    em.out = nullptr; em.rec = nullptr; em.op = 0; em.cap = 0; em.last_end = 0; em.nrec = 0; em.acc_lo = em.acc_hi = 0; em.dirty = false;
     for (;;) {
         if (state == ST_DONE) {
             if (have_unit) {                                                             // retire the finished unit
+                em.finish();
                 if (status == SWC_OK && (u64)em.op > cap64) status = SWC_ERR_OUTPUT_OVERFLOW;
                 a.consumed_bits[unit] = br.pos - sp.pos0;
                 a.out_len[unit] = em.op;
                 a.status[unit] = status;
-                a.rec_count[unit] = 0;                                                   // nothing for lz_resolve_kernel to replay
+                a.rec_count[unit] = em.nrec;
                 have_unit = false;
             }
             if (!exhausted) {
@@ -600,8 +555,9 @@ inflate_fused_kernel(BatchArgs a) {
                     const u64 in_len = a.in_len[unit];
                     cap64 = a.out_cap[unit];
                     em.out = a.out_base + a.out_off[unit];
+                    em.rec = a.rec_base + rec_start(a.out_off[unit]);
                     em.cap = cap64 > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (u32)cap64;
-                    em.op = 0;
+                    em.op = 0; em.last_end = 0; em.nrec = 0; em.acc_lo = em.acc_hi = 0; em.dirty = false;
                     const u32 bitskip = a.start_bits ? a.start_bits[unit] : 0;
                     sp.ubeg = a.in_base + a.in_off[unit];
                     sp.uend = sp.ubeg + in_len;
@@ -631,51 +587,15 @@ inflate_fused_kernel(BatchArgs a) {
                 em.literal(e);
             }
         }
+        // Lanes leave the loop at different steps: re-converge them here, or the compiler threads each break edge straight into
+        // the parked code and the warp executes it once per leaving group (measured: 3 x per round at 5 of 32 lanes).
+        __syncwarp();
         // ---- parked: lengths, distances, end of block, long codes ----
-        Match mt; mt.len = 0; mt.dist = 0;
         if (state == ST_PARKED) {
-            const int r = parked_step(br, em, M, bc, sp, lut, state, pend, mt);
-            if (r) { status = r; state = ST_DONE; mt.len = 0; }
+            const int r = parked_step(br, em, M, bc, sp, lut, state, pend);
+            if (r) { status = r; state = ST_DONE; }
         }
-        // ---- post this round's fragment and match to the copier warp ----
-        const bool copy = mt.len != 0 && (u64)em.op + em.nf + mt.len <= em.cap;
-        const u32 fm = __ballot_sync(SWC_FULL, em.nf != 0), cm = __ballot_sync(SWC_FULL, copy);
-        if (fm | cm) {
-            const u32 s = qk % QSLOTS, ph = (qk / QSLOTS) & 1;
-            mbar_wait(bars + (QSLOTS + s) * 8, ph ^ 1);                                  // slot released by the copier (first lap: free)
-            u8 *slot = queue + s * SLOT_BYTES;
-            if (em.nf) {
-                const u32 room = em.op < em.cap ? em.cap - em.op : 0u;
-                const u32 nw = em.nf < room ? em.nf : room;                              // bytes that fit the capacity
-                const u32 sh = 8 * (8 - em.nf);                                          // bring the first literal down to byte 0
-                u32 lo, hi;
-                if (sh >= 32) { lo = em.acc_hi >> (sh - 32); hi = 0; }
-                else { lo = __funnelshift_r(em.acc_lo, em.acc_hi, sh); hi = em.acc_hi >> sh; }
-                const u8 *dst = em.out + em.op;
-                ((uint4 *)(slot + 512))[__popc(fm & lt_mask)] = make_uint4((u32)(uintptr_t)dst, (u32)((uintptr_t)dst >> 32) | (nw << 24), lo, hi);
-                em.op += em.nf;
-                em.nf = 0;
-            }
-            u32 incl = copy ? mt.len : 0u;                                                // prefix sums of the match lengths, lane order = entry order
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const u32 up = __shfl_up_sync(SWC_FULL, incl, d);
-                if (lane >= (u32)d) incl += up;
-            }
-            const u32 total = __shfl_sync(SWC_FULL, incl, 31);
-            if (copy) {
-                const u8 *dst = em.out + em.op;
-                ((uint4 *)slot)[__popc(cm & lt_mask)] = make_uint4((u32)(uintptr_t)dst, (u32)((uintptr_t)dst >> 32), mt.len | (mt.dist << 16), incl - mt.len);
-                const u8 *src = dst - mt.dist;                                           // start the source sectors on their way into L2
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (mt.len < mt.dist ? mt.len : mt.dist) - 1));
-            }
-            if (lane == 0) *(uint2 *)(slot + 1024) = make_uint2(__popc(cm) | (__popc(fm) << 8), total);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bars + s * 8);
-            qk++;
-        }
-        em.op += mt.len;
+        __syncwarp();
         // ---- header: lanes at a block boundary ----
         if (state == ST_HEADER) {
             HeaderBits hb;
@@ -690,31 +610,25 @@ inflate_fused_kernel(BatchArgs a) {
             }
         }
     }
-    // tell the copier to stop
-    {
-        const u32 s = qk % QSLOTS, ph = (qk / QSLOTS) & 1;
-        mbar_wait(bars + (QSLOTS + s) * 8, ph ^ 1);
-        if (lane == 0) { *(uint2 *)(queue + s * SLOT_BYTES + 1024) = make_uint2(Q_DONE, 0); mbar_arrive(bars + s * 8); }
-    }
 }
 
-}  // namespace k1f
+}  // namespace k1l
 
-int launch_fused(const BatchArgs &a, cudaStream_t stream) {
+int launch_lut(const BatchArgs &a, cudaStream_t stream) {
     int dev = 0;
     SWC_CUDA_TRY(cudaGetDevice(&dev));
     static bool configured[64] = {};
     static int num_sms[64] = {};
     if (!configured[dev & 63]) {
-        SWC_CUDA_TRY(cudaFuncSetAttribute(k1f::inflate_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1f::SMEM_BYTES));
+        SWC_CUDA_TRY(cudaFuncSetAttribute(k1l::inflate_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1l::SMEM_BYTES));
         SWC_CUDA_TRY(cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
         configured[dev & 63] = true;
     }
-    const u64 per_cta = k1f::NP * 32;                                        // decoder lanes per CTA
+    const u64 per_cta = k1l::WARPS_PER_CTA * 32;
     u64 grid = (a.n + per_cta - 1) / per_cta;
-    const u64 resident = (u64)num_sms[dev & 63] * 2;                         // persistent lanes: one CTA per resident slot
+    const u64 resident = (u64)num_sms[dev & 63] * k1l::CTAS_PER_SM;          // persistent lanes: one CTA per resident slot
     if (grid > resident) grid = resident;
-    k1f::inflate_fused_kernel<<<(unsigned)grid, k1f::NP * 64, k1f::SMEM_BYTES, stream>>>(a);
+    k1l::inflate_lut_kernel<<<(unsigned)grid, k1l::WARPS_PER_CTA * 32, k1l::SMEM_BYTES, stream>>>(a);
     count_launch();
     return SWC_OK;
 }

@@ -221,9 +221,9 @@ def test_large_batch_thread_kernel(oracle):
             assert st[j] == ost, (j, i, st[j], ost)
 
 
-def test_benched_config_fused_kernel_all_units(oracle):
+def test_benched_config_lut_kernel_all_units(oracle):
     """BASELINE configs[1] shape through the kernels bench.py times: >= 20 000 units of 65 536-byte single dynamic-Huffman
-    blocks take the fused thread-per-unit LUT decoder with warp-cooperative match copies (inflate_lut.cu).  Every one of the
+    blocks take the thread-per-unit table-lookup decoder (inflate_lut.cu) + the record-replay kernel.  Every one of the
     512 distinct units is compared byte for byte (and its consumed bit count) with the oracle, and every tiled copy with the
     first copy on the device."""
     import torch

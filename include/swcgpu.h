@@ -14,9 +14,11 @@
  *   - every decode reports how much input it consumed, because the reference's wrappers keep parsing after the
  *     payload (GzipArchive.swift:88-94, ZlibArchive.swift:31-37, ZipContainer.swift:74-79, XZBlock.swift:78-82).
  *   - there is no CPU fallback: without a CUDA device every call returns SWC_ERR_NO_DEVICE.
- *   - threading: the library keeps one set of grow-only scratch arenas and pinned bounce buffers per device, so calls that
- *     use them (everything except the *_batch calls with caller-provided scratch) must not run concurrently on the same
- *     device from several host threads; one process per GPU (or external serialisation) is the supported model.
+ *   - threading: like the reference, the library may be called from any number of host threads.  Mutable state is one lazily
+ *     created context per device (scratch arenas, staging streams, pinned result buffers) behind a per-device mutex: calls on
+ *     the same device are serialised, calls on different devices run concurrently.  The asynchronous *_batch calls only hold
+ *     the mutex while they enqueue; when several of them are in flight on one device at the same time each needs its own
+ *     `scratch` (the NULL = library-pool form shares one arena).
  *   - multi-member / multi-stream / multi-block archives are discovered up front and decoded as one batch; the
  *     reference's in-order walk is kept as the validator, so results and errors are those of the sequential loop.
  *
@@ -120,6 +122,14 @@ int32_t swc_lzma_decompress_raw(const uint8_t *in, size_t in_len, int32_t lc, in
                                 int64_t dictionary_size, int64_t uncompressed_size /* <0 = nil */,
                                 uint8_t **out, size_t *out_len, size_t *consumed_bytes);
 int32_t swc_lzma2_decompress(const uint8_t *in, size_t in_len, uint8_t **out, size_t *out_len, size_t *consumed_bytes);
+/* one raw LZMA stream per unit (the ZIP / 7-Zip form, LZMA.decompress(data:properties:uncompressedSize:), LZMA.swift:56-61):
+ * props[i] = lc | lp << 8 | pb << 16, dict_size[i] as in LZMAProperties, uncompressed_size[i] < 0 = nil (end marker).
+ * lc + lp must be <= 4 in the batched form (the literal coders live in shared memory); other units report SWC_ERR_UNSUPPORTED. */
+int32_t swc_lzma_decompress_batch(const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len,
+                                  const uint32_t *props, const int64_t *dict_size, const int64_t *uncompressed_size,
+                                  uint8_t *out_base, const uint64_t *out_off, const uint64_t *out_cap,
+                                  uint64_t *out_len, uint64_t *consumed_bytes, int32_t *status,
+                                  uint64_t n, void *cuda_stream);
 /* one raw LZMA2 stream per unit; dict_bytes[i] is the XZ filter property byte */
 int32_t swc_lzma2_decompress_batch(const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len,
                                    const uint8_t *dict_bytes,
@@ -131,7 +141,36 @@ int32_t swc_lzma2_decompress_batch(const uint8_t *in_base, const uint64_t *in_of
  * GzipArchive.unarchive(archive:) / multiUnarchive   Sources/GZip/GzipArchive.swift:38-77
  * ZlibArchive.unarchive(archive:)                     Sources/Zlib/ZlibArchive.swift:25-42
  * XZArchive.unarchive(archive:) / splitUnarchive      Sources/XZ/XZArchive.swift:27-88 */
+/* GzipHeader(archive:) / GzipHeader.init(_: LsbBitReader)   Sources/GZip/GzipHeader.swift:10-60, 63-199
+ * ZlibHeader(archive:)                                       Sources/Zlib/ZlibHeader.swift:10-40, 42-93
+ * Pure framing: these two calls need no device.  String / extra-field bytes are returned as offsets into `in`
+ * (file name and comment are ISO-Latin-1, GzipHeader.swift:160,178; extra fields are the SI1 SI2 LEN data... records). */
+typedef struct swc_gzip_header {
+    int32_t  compression_method;     /* CompressionMethod.deflate = 8 */
+    uint32_t modification_time;      /* MTIME; 0 = nil */
+    uint8_t  os_type;                /* raw OS byte (FileSystemType(rawOsType)) */
+    uint8_t  is_text_file;           /* FTEXT */
+    uint8_t  has_file_name, has_comment;
+    size_t   file_name_off, file_name_len;     /* without the terminating zero */
+    size_t   comment_off, comment_len;
+    size_t   extra_off, extra_len;             /* the XLEN bytes behind the XLEN field (0,0 without FEXTRA) */
+    size_t   header_len;                       /* bytes from the member start to the first Deflate byte */
+} swc_gzip_header;
+typedef struct swc_zlib_header {
+    int32_t compression_method;      /* always 8 */
+    int32_t compression_level;       /* ZlibHeader.CompressionLevel raw value 0..3 */
+    int32_t window_size;             /* 1 << (CINFO + 8) */
+    size_t  header_len;              /* 2, or 6 with FDICT */
+} swc_zlib_header;
+int32_t swc_gzip_header_parse(const uint8_t *in, size_t in_len, size_t member_off, swc_gzip_header *hdr);
+int32_t swc_zlib_header_parse(const uint8_t *in, size_t in_len, swc_zlib_header *hdr);
 int32_t swc_gzip_unarchive(const uint8_t *in, size_t in_len, uint8_t **out, size_t *out_len, size_t *consumed_bytes);
+/* GzipArchive.multiUnarchive -> [Member] (GzipArchive.swift:13-22, 52-77): as swc_gzip_multi_unarchive, plus the offset of
+ * every member inside `in` (n_members + 1 entries, the last one = where the walk stopped) so the caller can rebuild
+ * Member.header with swc_gzip_header_parse.  On SWC_GZIP_WRONG_CRC the failing member is the last one returned. */
+int32_t swc_gzip_multi_unarchive_members(const uint8_t *in, size_t in_len,
+                                         uint8_t **out, size_t *out_len, size_t **member_ends, size_t **member_in_off,
+                                         size_t *n_members);
 int32_t swc_gzip_multi_unarchive(const uint8_t *in, size_t in_len,
                                  uint8_t **out, size_t *out_len, size_t **member_ends, size_t *n_members);
 int32_t swc_zlib_unarchive(const uint8_t *in, size_t in_len, uint8_t **out, size_t *out_len);
@@ -149,6 +188,12 @@ int32_t swc_crc64(const uint8_t *in, size_t n, uint64_t *result);
 int32_t swc_adler32(const uint8_t *in, size_t n, uint32_t *result);
 int32_t swc_xxh32(const uint8_t *in, size_t n, uint32_t *result);
 int32_t swc_sha256(const uint8_t *in, size_t n, uint8_t digest[32]);
+/* batched epilogues on DEVICE buffers (asynchronous on `cuda_stream`): one result per unit in_base[off[i] .. off[i]+len[i]).
+ * `status` may be NULL; units whose status[i] != 0 are not read (their result is 0). */
+int32_t swc_crc32_batch(const uint8_t *in_base, const uint64_t *off, const uint64_t *len, const int32_t *status,
+                        uint32_t *result, uint64_t n, void *cuda_stream);
+int32_t swc_xxh32_batch(const uint8_t *in_base, const uint64_t *off, const uint64_t *len,
+                        uint32_t *result, uint64_t n, void *cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -70,6 +70,12 @@ def lib():
         L.swc_lzma2_decompress_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, u64, vp]
         L.swc_gzip_unarchive.argtypes = [vp, sz, C.POINTER(vp), szp, szp]
         L.swc_gzip_multi_unarchive.argtypes = [vp, sz, C.POINTER(vp), szp, C.POINTER(vp), szp]
+        L.swc_gzip_multi_unarchive_members.argtypes = [vp, sz, C.POINTER(vp), szp, C.POINTER(vp), C.POINTER(vp), szp]
+        L.swc_gzip_header_parse.argtypes = [vp, sz, sz, vp]
+        L.swc_zlib_header_parse.argtypes = [vp, sz, vp]
+        L.swc_lzma_decompress_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, u64, vp]
+        L.swc_crc32_batch.argtypes = [vp, vp, vp, vp, vp, u64, vp]
+        L.swc_xxh32_batch.argtypes = [vp, vp, vp, vp, u64, vp]
         L.swc_zlib_unarchive.argtypes = [vp, sz, C.POINTER(vp), szp]
         L.swc_xz_unarchive.argtypes = [vp, sz, C.POINTER(vp), szp]
         L.swc_xz_split_unarchive.argtypes = [vp, sz, C.POINTER(vp), szp, C.POINTER(vp), szp]

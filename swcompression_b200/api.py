@@ -8,12 +8,14 @@ meaning, same error cases), routed through the C ABI of libswcgpu.so.
     LZMA2.decompress(data:)                             LZMA2.decompress(data)
     LZ4.decompress(data:[dictionary:dictionaryID:])     LZ4.decompress(data[, dictionary, dictionaryID])
     LZ4.multiDecompress(data:dictionary:dictionaryID:)  LZ4.multiDecompress(...)
-    GzipArchive.unarchive / multiUnarchive              GzipArchive.unarchive / multiUnarchive
+    GzipArchive.unarchive / multiUnarchive -> [Member]  GzipArchive.unarchive / multiUnarchive -> [GzipArchive.Member]
+    GzipHeader(archive:) / ZlibHeader(archive:)         GzipHeader(archive) / ZlibHeader(archive)
     ZlibArchive.unarchive                               ZlibArchive.unarchive
     XZArchive.unarchive / splitUnarchive                XZArchive.unarchive / splitUnarchive
 """
 import ctypes as C
-from dataclasses import dataclass
+import datetime
+from dataclasses import dataclass, field
 
 from . import _lib
 from .errors import check, error_for
@@ -128,8 +130,75 @@ class LZ4:
         return _multi("swc_lz4_multi_decompress", data, *args)
 
 
+class _CGzipHeader(C.Structure):
+    _fields_ = [("compression_method", C.c_int32), ("modification_time", C.c_uint32), ("os_type", C.c_uint8),
+                ("is_text_file", C.c_uint8), ("has_file_name", C.c_uint8), ("has_comment", C.c_uint8),
+                ("file_name_off", C.c_size_t), ("file_name_len", C.c_size_t), ("comment_off", C.c_size_t),
+                ("comment_len", C.c_size_t), ("extra_off", C.c_size_t), ("extra_len", C.c_size_t), ("header_len", C.c_size_t)]
+
+
+class _CZlibHeader(C.Structure):
+    _fields_ = [("compression_method", C.c_int32), ("compression_level", C.c_int32), ("window_size", C.c_int32),
+                ("header_len", C.c_size_t)]
+
+
+@dataclass
+class ExtraField:
+    """GzipHeader.ExtraField (Sources/GZip/GzipHeader+ExtraField.swift)"""
+    si1: int
+    si2: int
+    bytes: bytes
+
+
+# FileSystemType(rawOsType), Sources/Common/FileSystemType.swift (gzip OS byte)
+_OS_TYPES = {0: "fat", 3: "unix", 7: "macintosh", 11: "ntfs"}
+
+
+class GzipHeader:
+    """Sources/GZip/GzipHeader.swift:10-60 — init(archive:) parses the header of the first member (:63-66)."""
+
+    def __init__(self, archive, _member_off=0):
+        data = bytes(archive)
+        buf, n = _lib.inbuf(data)
+        h = _CGzipHeader()
+        check(_lib.lib().swc_gzip_header_parse(buf, n, C.c_size_t(_member_off), C.byref(h)))
+        self.compressionMethod = "deflate"
+        self.modificationTime = (None if h.modification_time == 0 else
+                                 datetime.datetime.fromtimestamp(h.modification_time, datetime.timezone.utc))
+        self.osType = _OS_TYPES.get(h.os_type, "other")
+        self.fileName = data[h.file_name_off:h.file_name_off + h.file_name_len].decode("latin-1") if h.has_file_name else None
+        self.comment = data[h.comment_off:h.comment_off + h.comment_len].decode("latin-1") if h.has_comment else None
+        self.isTextFile = bool(h.is_text_file)
+        self.extraFields = []
+        p, end = h.extra_off, h.extra_off + h.extra_len
+        while p < end:
+            ln = data[p + 2] | data[p + 3] << 8
+            self.extraFields.append(ExtraField(data[p], data[p + 1], data[p + 4:p + 4 + ln]))
+            p += 4 + ln
+        self.headerLength = h.header_len
+
+
+class ZlibHeader:
+    """Sources/Zlib/ZlibHeader.swift:10-45"""
+    LEVELS = ("fastestAlgorithm", "fastAlgorithm", "defaultAlgorithm", "slowAlgorithm")
+
+    def __init__(self, archive):
+        buf, n = _lib.inbuf(archive)
+        h = _CZlibHeader()
+        check(_lib.lib().swc_zlib_header_parse(buf, n, C.byref(h)))
+        self.compressionMethod = "deflate"
+        self.compressionLevel = self.LEVELS[h.compression_level]
+        self.windowSize = h.window_size
+
+
 class GzipArchive:
-    """Sources/GZip/GzipArchive.swift:10-77 (members are returned as their data; header metadata is not on the hot path)"""
+    """Sources/GZip/GzipArchive.swift:10-77"""
+
+    @dataclass
+    class Member:
+        """GzipArchive.Member (GzipArchive.swift:13-22)"""
+        header: GzipHeader
+        data: bytes
 
     @staticmethod
     def unarchive(archive):
@@ -137,7 +206,22 @@ class GzipArchive:
 
     @staticmethod
     def multiUnarchive(archive):
-        return _multi("swc_gzip_multi_unarchive", archive)
+        """-> [Member]; GzipError.wrongCRC carries the members decoded so far, the failing one last (GzipArchive.swift:62-76)."""
+        L = _lib.lib()
+        data = bytes(archive)
+        buf, n = _lib.inbuf(data)
+        out, out_len, ends, offs, cnt = C.c_void_p(), C.c_size_t(0), C.c_void_p(), C.c_void_p(), C.c_size_t(0)
+        st = L.swc_gzip_multi_unarchive_members(buf, n, C.byref(out), C.byref(out_len), C.byref(ends), C.byref(offs), C.byref(cnt))
+        whole = _lib.take(out, out_len)
+        e = _lib.take_sizes(ends, cnt)
+        o = _lib.take_sizes(offs, C.c_size_t(cnt.value + 1)) if offs.value else []
+        members, prev = [], 0
+        for i, x in enumerate(e):
+            members.append(GzipArchive.Member(GzipHeader(data, _member_off=o[i]), whole[prev:x]))
+            prev = x
+        if st != 0:
+            raise error_for(st, members if st in _PAYLOAD_CODES else None)
+        return members
 
 
 class ZlibArchive:

@@ -74,9 +74,17 @@ int bzip2_stream_by_blocks(const uint8_t *in, const u8 *d_in, size_t in_len, siz
         h[k] = pos[k] >> 3; h[nb + k] = in_len - (pos[k] >> 3); h[2 * nb + k] = k * cap; h[3 * nb + k] = cap;
         h_sb[k] = (u8)(pos[k] & 7);
     }
+    // the block-parallel attempt needs nb x (cap + ~6 x cap of scratch); when that does not fit, the sequential decoder (which
+    // holds one block at a time) takes over instead of failing the call
+    {
+        size_t free_b = 0, total_b = 0;
+        SWC_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const size_t need = nb * (cap + bzip2::scratch_per_unit(cap)) + ((size_t)64 << 20);
+        if (need > free_b / 2) return SWC_OK;
+    }
     DevBuf d_out, d_meta;
-    if ((st = d_out.alloc(nb * cap + 64))) return st;
-    if ((st = d_meta.alloc(nb * 8 * 7 + nb * 4 + nb + 64))) return st;
+    if (d_out.alloc(nb * cap + 64)) return SWC_OK;
+    if (d_meta.alloc(nb * 8 * 7 + nb * 4 + nb + 64)) return SWC_OK;
     u64 *m = d_meta.as<u64>();
     int32_t *d_status = (int32_t *)(m + 7 * nb);
     u8 *d_sb = (u8 *)(d_status + nb);
@@ -87,7 +95,7 @@ int bzip2_stream_by_blocks(const uint8_t *in, const u8 *d_in, size_t in_len, siz
         std::vector<u64> soff(nb);
         for (size_t k = 0; k < nb; k++) { soff[k] = total; total += bzip2::scratch_per_unit(cap); }
         void *scratch = nullptr;
-        if ((st = scratch_get(total, &scratch, 0))) return st;
+        if (scratch_get(total, &scratch, 0)) return SWC_OK;
         SWC_CUDA_TRY(cudaMemcpy(scratch, soff.data(), nb * 8, cudaMemcpyHostToDevice));
         bzip2::Args a;
         a.in_base = d_in; a.in_off = m; a.in_len = m + nb;
@@ -180,6 +188,7 @@ int32_t swc_bzip2_decompress_batch(const uint8_t *in_base, const uint64_t *in_of
                                    uint64_t *out_len, uint64_t *consumed_bits, int32_t *status,
                                    uint64_t n, void *cuda_stream) {
     if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    ApiLock api_lock;
     return bzip2_batch_impl(in_base, in_off, in_len, out_base, out_off, out_cap, out_len, consumed_bits, status, n, (cudaStream_t)cuda_stream);
 }
 
@@ -191,6 +200,7 @@ int32_t swc_bzip2_decompress(const uint8_t *in, size_t in_len, size_t start_bit,
     if (consumed_bits) *consumed_bits = 0;
     if (start_bit & 7) return SWC_ERR_UNSUPPORTED;      // the reference's byte reads require an aligned reader (BZip2.swift:59)
     if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    ApiLock api_lock;
     DevBuf d_in;
     int st = upload(d_in, in, in_len);
     if (st) return st;
@@ -208,6 +218,7 @@ int32_t swc_bzip2_multi_decompress(const uint8_t *in, size_t in_len,
     if (!out || !out_len || !stream_ends || !n_streams) return SWC_ERR_INVALID_ARG;
     *out = nullptr; *out_len = 0; *stream_ends = nullptr; *n_streams = 0;
     if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    ApiLock api_lock;
     DevBuf d_in;
     int st = upload(d_in, in, in_len);
     if (st) return st;

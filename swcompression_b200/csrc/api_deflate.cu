@@ -94,6 +94,7 @@ int32_t swc_deflate_decompress_batch(const uint8_t *in_base, const uint64_t *in_
                                      uint64_t *out_len, uint64_t *consumed_bits, int32_t *status,
                                      uint64_t n, void *scratch, size_t scratch_bytes, void *cuda_stream) {
     if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    ApiLock api_lock;
     return deflate_batch_impl(in_base, in_off, in_len, start_bits, out_base, out_off, out_cap, out_capacity_total,
                               out_len, consumed_bits, status, n, scratch, scratch_bytes, (cudaStream_t)cuda_stream);
 }
@@ -107,22 +108,26 @@ int32_t swc_deflate_decompress_batch_host(const uint8_t *in_base, const uint64_t
                                           uint64_t out_total,
                                           uint64_t *out_len, uint64_t *consumed_bits, int32_t *status, uint64_t n) {
     if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    ApiLock api_lock;
     if (n == 0) return SWC_OK;
     if (!in_base || !in_off || !in_len || !out_base || !out_off || !out_cap || !out_len || !consumed_bits || !status) return SWC_ERR_INVALID_ARG;
-    static cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
-    static cudaEvent_t tables_ready = nullptr;
+    DeviceCtx &ctx = device_ctx();                                       // streams / event / pinned result buffer of THIS device
+    cudaStream_t *streams = ctx.streams;
     if (!streams[0]) {
-        for (auto &s : streams) SWC_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-        SWC_CUDA_TRY(cudaEventCreateWithFlags(&tables_ready, cudaEventDisableTiming));
+        for (int i = 0; i < 3; i++) SWC_CUDA_TRY(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking));
+        SWC_CUDA_TRY(cudaEventCreateWithFlags(&ctx.tables_ready, cudaEventDisableTiming));
     }
-    // slices need monotone, in-bounds offsets so that a slice is one contiguous byte range on both sides
+    cudaEvent_t tables_ready = ctx.tables_ready;
+    // every unit must lie inside the two arenas (checked for ALL units, without overflowing sums); slices additionally need
+    // monotone offsets so that a slice is one contiguous byte range on both sides
     bool monotone = true;
-    for (uint64_t i = 0; i < n && monotone; i++) {
-        if (in_off[i] + in_len[i] > in_total || out_off[i] + out_cap[i] > out_total) return SWC_ERR_INVALID_ARG;
+    for (uint64_t i = 0; i < n; i++) {
+        if (in_off[i] > in_total || in_len[i] > in_total - in_off[i] || out_off[i] > out_total || out_cap[i] > out_total - out_off[i])
+            return SWC_ERR_INVALID_ARG;
+        if (out_off[i] & 15) return SWC_ERR_INVALID_ARG;
         if (i && (in_off[i] < in_off[i - 1] + in_len[i - 1] || out_off[i] < out_off[i - 1] + out_cap[i - 1])) monotone = false;
     }
-    static int s_env = -1;
-    if (s_env < 0) { const char *e = getenv("SWC_HOST_SLICES"); s_env = e ? atoi(e) : 0; }
+    static const int s_env = [] { const char *e = getenv("SWC_HOST_SLICES"); return e ? atoi(e) : 0; }();
     // slice count: ~2048 units per slice keeps the warp-per-unit decoder's grid full while the first device->host copy can
     // start after 1/32 of the batch (measured on 65536 x 64 KiB units: 8 slices 37.8, 16 slices 41.2, 32 slices 42.1 GB/s)
     uint64_t S = 1;
@@ -137,14 +142,14 @@ int32_t swc_deflate_decompress_batch_host(const uint8_t *in_base, const uint64_t
     if ((st = arena_get(0, hdr + (out_total / 3 + 2) * 4 + 256, &p_scr, 0))) return st;
     // result tables come back through a library-owned pinned buffer: a D2H into pageable caller memory would block the
     // host thread inside the slice loop and serialise the whole pipeline
-    static u8 *h_res = nullptr; static size_t h_res_bytes = 0;
     const size_t res_bytes = n * 20;
-    if (h_res_bytes < res_bytes) {
-        if (h_res) cudaFreeHost(h_res);
-        h_res = nullptr; h_res_bytes = 0;
-        SWC_CUDA_TRY(cudaMallocHost((void **)&h_res, res_bytes + (res_bytes >> 2)));
-        h_res_bytes = res_bytes + (res_bytes >> 2);
+    if (ctx.h_res_bytes < res_bytes) {
+        if (ctx.h_res) cudaFreeHost(ctx.h_res);
+        ctx.h_res = nullptr; ctx.h_res_bytes = 0;
+        SWC_CUDA_TRY(cudaMallocHost((void **)&ctx.h_res, res_bytes + (res_bytes >> 2)));
+        ctx.h_res_bytes = res_bytes + (res_bytes >> 2);
     }
+    u8 *h_res = ctx.h_res;
     u64 *h_out_len = (u64 *)h_res, *h_cons = h_out_len + n;
     int32_t *h_status = (int32_t *)(h_cons + n);
     u8 *m = (u8 *)p_meta;
@@ -177,7 +182,7 @@ int32_t swc_deflate_decompress_batch_host(const uint8_t *in_base, const uint64_t
         SWC_CUDA_TRY(cudaMemcpyAsync(h_cons + b, d_cons + b, (e - b) * 8, cudaMemcpyDeviceToHost, s));
         SWC_CUDA_TRY(cudaMemcpyAsync(h_status + b, d_status + b, (e - b) * 4, cudaMemcpyDeviceToHost, s));
     }
-    for (auto &s : streams) SWC_CUDA_TRY(cudaStreamSynchronize(s));
+    for (int i = 0; i < 3; i++) SWC_CUDA_TRY(cudaStreamSynchronize(streams[i]));
     memcpy(out_len, h_out_len, n * 8);
     memcpy(consumed_bits, h_cons, n * 8);
     memcpy(status, h_status, n * 4);
@@ -190,6 +195,7 @@ int32_t swc_deflate_decompress(const uint8_t *in, size_t in_len, size_t start_bi
     *out = nullptr; *out_len = 0;
     if (consumed_bits) *consumed_bits = 0;
     if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    ApiLock api_lock;
     DevBuf d_in;
     int st = d_in.alloc(round16(in_len) + 16);
     if (st) return st;

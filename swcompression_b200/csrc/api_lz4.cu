@@ -48,7 +48,14 @@ int run_blocks(DeviceInput &dev, const std::vector<Block> &blocks, int mode, boo
     std::vector<uint64_t> h_off(nb), h_len(nb), u_off(nunits), u_cap(nunits);
     std::vector<uint32_t> h_first(nunits), h_cnt(nunits);
     for (size_t i = 0; i < nb; i++) { h_off[i] = blocks[i].off; h_len[i] = blocks[i].len | (blocks[i].stored ? 1ull << 63 : 0); }
-    auto cap_of = [&](size_t i) { return round16(blocks[i].stored ? blocks[i].len : max_block); };
+    // first-attempt capacity: the frame's block size, but never more than an LZ4 block of that many bytes can expand to
+    // (each input byte adds at most 255 output bytes) — frames made of many tiny flushed blocks would otherwise ask for
+    // nb x 4 MiB; a block that decodes to more than this reports the size it needs and is redone (overflow retry below)
+    auto cap_of = [&](size_t i) {
+        if (blocks[i].stored) return round16(blocks[i].len);
+        const size_t expand = blocks[i].len < (max_block / 255 + 1) ? blocks[i].len * 255 + 64 : max_block;
+        return round16(expand < max_block ? expand : max_block);
+    };
     size_t total = 0;
     if (mode == 0) {
         for (size_t i = 0; i < nb; i++) { u_off[i] = total; u_cap[i] = cap_of(i); total += u_cap[i]; h_first[i] = (uint32_t)i; h_cnt[i] = 1; }
@@ -272,6 +279,7 @@ int32_t swc_lz4_block_decompress_batch(const uint8_t *in_base, const uint64_t *i
                                        uint8_t *out_base, const uint64_t *out_off, const uint64_t *out_cap,
                                        uint64_t *out_len, int32_t *status, uint64_t n, void *cuda_stream) {
     if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    ApiLock api_lock;
     if (n == 0) return SWC_OK;
     if (!in_base || !in_off || !in_len || !out_base || !out_off || !out_cap || !out_len || !status) return SWC_ERR_INVALID_ARG;
     lz4::Args a;
@@ -299,7 +307,12 @@ int32_t swc_lz4_block_decompress_batch_host(const uint8_t *in_base, const uint64
                                             uint64_t out_total,
                                             uint64_t *out_len, int32_t *status, uint64_t n) {
     if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    ApiLock api_lock;
     if (n == 0) return SWC_OK;
+    if (!in_base || !in_off || !in_len || !out_base || !out_off || !out_cap || !out_len || !status) return SWC_ERR_INVALID_ARG;
+    for (uint64_t i = 0; i < n; i++)                                       // every unit inside the two arenas, overflow-safe
+        if (in_off[i] > in_total || in_len[i] > in_total - in_off[i] || out_off[i] > out_total || out_cap[i] > out_total - out_off[i] || (out_off[i] & 15))
+            return SWC_ERR_INVALID_ARG;
     DevBuf d_in, d_out, d_meta;
     int st;
     if ((st = d_in.alloc(round16(in_total) + 32))) return st;
@@ -330,6 +343,7 @@ int32_t swc_lz4_decompress(const uint8_t *in, size_t in_len, const uint8_t *dict
     *out = nullptr; *out_len = 0;
     if (consumed_bytes) *consumed_bytes = 0;
     if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    ApiLock api_lock;
     size_t base = 0;
     bool have_dict = dict != nullptr;
     for (;;) {
@@ -365,6 +379,7 @@ int32_t swc_lz4_multi_decompress(const uint8_t *in, size_t in_len, const uint8_t
     if (!out || !out_len || !frame_ends || !n_frames) return SWC_ERR_INVALID_ARG;
     *out = nullptr; *out_len = 0; *frame_ends = nullptr; *n_frames = 0;
     if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    ApiLock api_lock;
     DeviceInput dev;
     bool uploaded = false;
     std::vector<uint8_t> o;

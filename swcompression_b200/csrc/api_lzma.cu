@@ -325,9 +325,12 @@ void xz_prefetch(const uint8_t *in, size_t n, const u8 *d_in, Prefetch &pf) {
         if (multibyte(ir, &count) || count < 0 || count > 1000000) break;
         std::vector<std::pair<int64_t, int64_t>> recs((size_t)count);
         bool bad = false; uint64_t blocks_total = 0;
-        for (auto &rc : recs) {
-            if (multibyte(ir, &rc.first) || multibyte(ir, &rc.second) || rc.first <= 0) { bad = true; break; }
-            blocks_total += ((uint64_t)rc.first + 3) & ~3ull;
+        for (auto &rc : recs) {                                   // untrusted sizes: every sum is checked against the bytes before the index
+            if (multibyte(ir, &rc.first) || multibyte(ir, &rc.second) || rc.first <= 0 || rc.second < 0) { bad = true; break; }
+            if ((uint64_t)rc.first > (uint64_t)istart) { bad = true; break; }
+            const uint64_t padded = ((uint64_t)rc.first + 3) & ~3ull;
+            if (padded > (uint64_t)istart - blocks_total) { bad = true; break; }
+            blocks_total += padded;
         }
         if (bad || blocks_total + 12 > istart) break;
         const size_t sstart = istart - (size_t)blocks_total - 12;
@@ -335,7 +338,9 @@ void xz_prefetch(const uint8_t *in, size_t n, const u8 *d_in, Prefetch &pf) {
         if (memcmp(in + sstart, magic, 6) != 0) break;
         size_t boff = sstart + 12;
         for (auto &rc : recs) {
+            if (boff + 2 > istart) { bad = true; break; }
             const size_t hsz = ((size_t)in[boff] + 1) * 4;
+            if (hsz > istart - boff) { bad = true; break; }
             // single LZMA2 filter, optional size fields: flags, [comp], [uncomp], id 0x21, props size 1, dict byte
             Rd hr{in, boff + hsz, boff + 1};
             const unsigned flags = in[boff + 1]; hr.off = boff + 2;
@@ -347,11 +352,15 @@ void xz_prefetch(const uint8_t *in, size_t n, const u8 *d_in, Prefetch &pf) {
             }
             boff += ((size_t)rc.first + 3) & ~(size_t)3;
         }
+        if (bad) break;
         pos = sstart;
     }
     if (blks.size() < 2) return;                          // nothing to gain
     uint64_t total = 0;
-    for (auto &b : blks) total += round16(b.uncomp + 16);
+    for (auto &b : blks) {
+        if (b.uncomp > ((uint64_t)48 << 30)) return;
+        total += round16(b.uncomp + 16);
+    }
     if (total > ((uint64_t)48 << 30)) return;
     const size_t nb = blks.size();
     std::vector<uint64_t> h_off(nb), h_len(nb), o_off(nb), o_cap(nb);
@@ -440,6 +449,7 @@ int32_t swc_lzma_decompress(const uint8_t *in, size_t in_len, uint8_t **out, siz
     for (int i = 0; i < 8; i++) us |= (uint64_t)in[5 + i] << (8 * i);
     job.usize = (i64)us;
     if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    ApiLock api_lock;
     const size_t hint = job.usize >= 0 && job.usize < ((i64)1 << 36) ? (size_t)job.usize + 16 : 0;
     return single(in, in_len, 13, job, hint, out, out_len, consumed_bytes, 13);
 }
@@ -453,6 +463,7 @@ int32_t swc_lzma_decompress_raw(const uint8_t *in, size_t in_len, int32_t lc, in
     if (consumed_bytes) *consumed_bytes = 0;
     if (lc < 0 || lp < 0 || pb < 0 || lc > 8 || lp > 4 || pb > 4) return SWC_ERR_REFERENCE_TRAP;   // "no validation": OOB in the reference
     if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    ApiLock api_lock;
     LzmaJob job; job.mode = lzma::MODE_RAW; job.dict_byte = 0;
     job.props = (u32)lc | ((u32)lp << 8) | ((u32)pb << 16);
     job.dict_size = dictionary_size; job.usize = uncompressed_size < 0 ? -1 : uncompressed_size;
@@ -467,8 +478,28 @@ int32_t swc_lzma2_decompress(const uint8_t *in, size_t in_len, uint8_t **out, si
     if (consumed_bytes) *consumed_bytes = 0;
     if (in_len < 1) return SWC_LZMA_RANGE_DECODER_INIT_ERROR;
     if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    ApiLock api_lock;
     LzmaJob job; job.mode = lzma::MODE_LZMA2; job.dict_byte = in[0]; job.props = 0; job.dict_size = 0; job.usize = -1;
     return single(in, in_len, 1, job, 0, out, out_len, consumed_bytes, 1);
+}
+
+int32_t swc_lzma_decompress_batch(const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len,
+                                  const uint32_t *props, const int64_t *dict_size, const int64_t *uncompressed_size,
+                                  uint8_t *out_base, const uint64_t *out_off, const uint64_t *out_cap,
+                                  uint64_t *out_len, uint64_t *consumed_bytes, int32_t *status,
+                                  uint64_t n, void *cuda_stream) {
+    if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    ApiLock api_lock;
+    if (n == 0) return SWC_OK;
+    if (!in_base || !in_off || !in_len || !props || !dict_size || !uncompressed_size || !out_base || !out_off || !out_cap || !out_len ||
+        !consumed_bytes || !status)
+        return SWC_ERR_INVALID_ARG;
+    lzma::Args a;
+    a.mode = lzma::MODE_RAW; a.in_base = in_base; a.in_off = in_off; a.in_len = in_len; a.dict_bytes = nullptr;
+    a.props = props; a.dict_size = (const i64 *)dict_size; a.usize = (const i64 *)uncompressed_size;
+    a.out_base = out_base; a.out_off = out_off; a.out_cap = out_cap; a.out_len = out_len; a.consumed = consumed_bytes;
+    a.status = status; a.n = n; a.lit_scratch = nullptr;      // lc + lp > 4 would need 6 MB of literal coders per unit: refused here
+    return lzma::launch(a, (cudaStream_t)cuda_stream);
 }
 
 int32_t swc_lzma2_decompress_batch(const uint8_t *in_base, const uint64_t *in_off, const uint64_t *in_len,
@@ -477,6 +508,7 @@ int32_t swc_lzma2_decompress_batch(const uint8_t *in_base, const uint64_t *in_of
                                    uint64_t *out_len, uint64_t *consumed_bytes, int32_t *status,
                                    uint64_t n, void *cuda_stream) {
     if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    ApiLock api_lock;
     if (n == 0) return SWC_OK;
     if (!in_base || !in_off || !in_len || !dict_bytes || !out_base || !out_off || !out_cap || !out_len || !consumed_bytes || !status)
         return SWC_ERR_INVALID_ARG;
@@ -492,6 +524,7 @@ int32_t swc_xz_unarchive(const uint8_t *in, size_t in_len, uint8_t **out, size_t
     if (!out || !out_len) return SWC_ERR_INVALID_ARG;
     *out = nullptr; *out_len = 0;
     if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    ApiLock api_lock;
     std::vector<uint8_t> o; std::vector<size_t> ends;
     int st = xz_all(in, in_len, o, ends);
     if (st != SWC_OK && st != SWC_XZ_WRONG_CHECK) return st;
@@ -504,6 +537,7 @@ int32_t swc_xz_split_unarchive(const uint8_t *in, size_t in_len,
     if (!out || !out_len || !stream_ends || !n_streams) return SWC_ERR_INVALID_ARG;
     *out = nullptr; *out_len = 0; *stream_ends = nullptr; *n_streams = 0;
     if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    ApiLock api_lock;
     std::vector<uint8_t> o; std::vector<size_t> ends;
     int st = xz_all(in, in_len, o, ends);
     if (st != SWC_OK && st != SWC_XZ_WRONG_CHECK) return st;

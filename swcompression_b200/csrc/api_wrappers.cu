@@ -62,44 +62,101 @@ uint32_t crc32_header(const uint8_t *p, size_t n) {
     return ~c;
 }
 
-// GzipHeader.init(_:) GzipHeader.swift:68-199
-int gzip_header(const uint8_t *in, size_t n, size_t *off) {
-    size_t p = *off;
-    if (n - p < 10) return SWC_GZIP_WRONG_MAGIC;
-    if (in[p] != 0x1f || in[p + 1] != 0x8b) return SWC_GZIP_WRONG_MAGIC;
-    if (in[p + 2] != 8) return SWC_GZIP_WRONG_COMPRESSION_METHOD;
-    const unsigned flags = in[p + 3];
-    if (flags & 0xE0) return SWC_GZIP_WRONG_FLAGS;
-    const size_t hstart = p;
-    p += 10;
-    if (flags & 0x04) {                                             // FEXTRA
-        if (n - p < 2) return SWC_GZIP_WRONG_MAGIC;
-        long xlen = in[p] | in[p + 1] << 8; p += 2;
-        if (!((long)(n - p) >= xlen && xlen >= 4)) return SWC_GZIP_WRONG_MAGIC;
-        while (xlen > 0) {
-            if (n - p < 4) return SWC_ERR_REFERENCE_TRAP;           // unguarded reads past the end trap in the reference
-            if (in[p + 1] == 0) return SWC_GZIP_WRONG_FLAGS;
-            long len = in[p + 2] | in[p + 3] << 8; p += 4;
-            xlen -= 4;
-            if (xlen < len) return SWC_GZIP_WRONG_MAGIC;
-            if ((long)(n - p) < len) return SWC_ERR_REFERENCE_TRAP;
-            p += (size_t)len; xlen -= len;
+// GzipHeader.init(_: LsbBitReader), GzipHeader.swift:68-199 — one pass over the member's header that both validates it and
+// records where its fields are.  Written against the Swift source (guards in source order, one `Cursor` read per
+// `reader.byte()`); `left()` is `reader.bytesLeft`.  Reads the reference performs WITHOUT a guard trap there (BitByteData
+// precondition): they report SWC_ERR_REFERENCE_TRAP here.
+struct Cursor {
+    const uint8_t *base; size_t n, at;
+    size_t left() const { return n - at; }
+    bool finished() const { return at >= n; }
+};
+
+int gzip_parse(const uint8_t *in, size_t n, size_t member_off, swc_gzip_header *h) {
+    if (member_off > n) return SWC_GZIP_WRONG_MAGIC;
+    Cursor c{in, n, member_off};
+    swc_gzip_header out;
+    memset(&out, 0, sizeof(out));
+    if (c.left() < 10) return SWC_GZIP_WRONG_MAGIC;                                  // :70-71
+    if (in[c.at] != 0x1f || in[c.at + 1] != 0x8b) return SWC_GZIP_WRONG_MAGIC;       // :74-76 (uint16 == 0x8b1f)
+    if (in[c.at + 2] != 8) return SWC_GZIP_WRONG_COMPRESSION_METHOD;                 // :80-82
+    out.compression_method = 8;
+    const unsigned flg = in[c.at + 3];
+    if ((flg & 0xE0) != 0) return SWC_GZIP_WRONG_FLAGS;                              // :86-88
+    out.modification_time = (uint32_t)in[c.at + 4] | (uint32_t)in[c.at + 5] << 8 | (uint32_t)in[c.at + 6] << 16 | (uint32_t)in[c.at + 7] << 24;
+    out.os_type = in[c.at + 9];                                                      // :103-105 (XFL at +8 is only hashed)
+    out.is_text_file = (flg & 0x01) != 0;                                            // :107
+    c.at += 10;
+    if (flg & 0x04) {                                                                // FEXTRA :111-155
+        if (c.left() < 2) return SWC_GZIP_WRONG_MAGIC;                               // :112-113
+        size_t xlen = (size_t)in[c.at] | (size_t)in[c.at + 1] << 8;
+        c.at += 2;
+        if (!(c.left() >= xlen && xlen >= 4)) return SWC_GZIP_WRONG_MAGIC;           // :123-124
+        out.extra_off = c.at; out.extra_len = xlen;
+        long remaining = (long)xlen;                                                 // the reference's signed `xlen` countdown
+        while (remaining > 0) {                                                      // :125
+            // si1, si2, two length bytes: four unguarded reader.byte() calls (:126-140)
+            if (c.left() < 2) return SWC_ERR_REFERENCE_TRAP;
+            if (in[c.at + 1] == 0) return SWC_GZIP_WRONG_FLAGS;                      // :131-132 (checked before the length is read)
+            if (c.left() < 4) return SWC_ERR_REFERENCE_TRAP;
+            const long len = (long)in[c.at + 2] | (long)in[c.at + 3] << 8;
+            c.at += 4;
+            remaining -= 4;                                                          // :141
+            if (remaining < len) return SWC_GZIP_WRONG_MAGIC;                        // :145-146
+            if ((long)c.left() < len) return SWC_ERR_REFERENCE_TRAP;                 // :148-152 unguarded payload reads
+            c.at += (size_t)len;
+            remaining -= len;                                                        // :154
         }
     }
-    for (unsigned bit : {0x08u, 0x10u}) {                           // FNAME, FCOMMENT
-        if (!(flags & bit)) continue;
+    if (flg & 0x08) {                                                                // FNAME :159-172
+        out.has_file_name = 1; out.file_name_off = c.at;
         for (;;) {
-            if (p >= n) return SWC_GZIP_WRONG_MAGIC;
-            if (in[p++] == 0) break;
+            if (c.finished()) return SWC_GZIP_WRONG_MAGIC;                           // :162-163
+            if (in[c.at++] == 0) break;
         }
+        out.file_name_len = c.at - 1 - out.file_name_off;
     }
-    if (flags & 0x02) {                                             // FHCRC
-        if (n - p < 2) return SWC_GZIP_WRONG_MAGIC;
-        unsigned crc16 = in[p] | in[p + 1] << 8;
-        if ((crc32_header(in + hstart, p - hstart) & 0xFFFF) != crc16) return SWC_GZIP_WRONG_HEADER_CRC;
-        p += 2;
+    if (flg & 0x10) {                                                                // FCOMMENT :177-190
+        out.has_comment = 1; out.comment_off = c.at;
+        for (;;) {
+            if (c.finished()) return SWC_GZIP_WRONG_MAGIC;                           // :180-181
+            if (in[c.at++] == 0) break;
+        }
+        out.comment_len = c.at - 1 - out.comment_off;
     }
-    *off = p;
+    if (flg & 0x02) {                                                                // FHCRC :194-200
+        if (c.left() < 2) return SWC_GZIP_WRONG_MAGIC;
+        const unsigned stored = (unsigned)in[c.at] | (unsigned)in[c.at + 1] << 8;
+        if ((crc32_header(in + member_off, c.at - member_off) & 0xFFFFu) != stored) return SWC_GZIP_WRONG_HEADER_CRC;
+        c.at += 2;
+    }
+    out.header_len = c.at - member_off;
+    if (h) *h = out;
+    return SWC_OK;
+}
+
+int gzip_header(const uint8_t *in, size_t n, size_t *off) {
+    swc_gzip_header h;
+    const int st = gzip_parse(in, n, *off, &h);
+    if (st == SWC_OK) *off += h.header_len;
+    return st;
+}
+
+// ZlibHeader.init(_: LsbBitReader), ZlibHeader.swift:47-93
+int zlib_parse(const uint8_t *in, size_t n, swc_zlib_header *h) {
+    if (n < 2) return SWC_ZLIB_WRONG_COMPRESSION_METHOD;                             // :49-50
+    const unsigned cmf = in[0], flg = in[1];
+    if ((cmf & 0xF) != 8) return SWC_ZLIB_WRONG_COMPRESSION_METHOD;                  // :56-58
+    const unsigned cinfo = (cmf & 0xF0) >> 4;
+    if (cinfo > 7) return SWC_ZLIB_WRONG_COMPRESSION_INFO;                           // :62-64
+    // CompressionLevel(rawValue: (flags & 0xC0) >> 6) covers 0...3: it cannot fail (:80-82)
+    if ((((unsigned)cmf << 8) + flg) % 31 != 0) return SWC_ZLIB_WRONG_FCHECK;        // :84-85 (Swift precedence: (cmf << 8) + flags)
+    size_t len = 2;
+    if ((flg & 0x20) != 0) {                                                         // FDICT: four bytes are skipped (:88-92)
+        if (n - 2 < 4) return SWC_ZLIB_WRONG_FCHECK;
+        len = 6;
+    }
+    if (h) { h->compression_method = 8; h->compression_level = (int32_t)((flg & 0xC0) >> 6); h->window_size = 1 << (cinfo + 8); h->header_len = len; }
     return SWC_OK;
 }
 
@@ -162,9 +219,11 @@ int gzip_member(const uint8_t *in, size_t n, const u8 *d_in, size_t *off, HostOu
 // trailer and produced ISIZE bytes — exactly what the sequential decoder would have computed from the same start.  A
 // member that does not validate (a signature look-alike inside its payload, ISIZE wrap-around, damage) is decoded by the
 // sequential path, and the walk resynchronises on the candidate list afterwards.
+static size_t inflate_scratch_bytes(u64 n, u64 out_total) { return swc_deflate_batch_scratch_bytes(n, out_total); }
+
 struct Cand { size_t at, dstart, next; uint32_t crc, isize; long unit; };
 
-int gzip_multi_batch(const uint8_t *in, size_t n, const u8 *d_in, HostOut &o, std::vector<size_t> &ends, size_t *off, int *result, bool *stop) {
+int gzip_multi_batch(const uint8_t *in, size_t n, const u8 *d_in, HostOut &o, std::vector<size_t> &ends, std::vector<size_t> &starts, size_t *off, int *result, bool *stop) {
     const bool trace = getenv("SWC_TRACE") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t0 = now();
@@ -177,7 +236,8 @@ int gzip_multi_batch(const uint8_t *in, size_t n, const u8 *d_in, HostOut &o, st
     if (pos.size() < 4 || pos[0] != 0) return SWC_OK;              // nothing to gain: the caller's loop handles it
     size_t free_b = 0, total_b = 0;
     SWC_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-    const size_t budget = free_b / 3;
+    // a round needs its speculative outputs, the 4/3 x record scratch of the Deflate batch and the gather copy: ~3.3 x out_total
+    const size_t budget = free_b / 5;
     cudaStream_t stream = 0;
     size_t idx = 0;
     while (idx < pos.size() && pos[idx] == *off && !*stop) {
@@ -212,9 +272,11 @@ int gzip_multi_batch(const uint8_t *in, size_t n, const u8 *d_in, HostOut &o, st
         DevBuf meta, d_out;
         u64 *m = nullptr;
         if (nu) {
+            // an allocation failure is not an error of the archive: hand the rest to the caller's sequential walk
             int st = meta.alloc(nu * 64);                               // 7 u64 arrays + status + crc
-            if (st) return st;
-            if ((st = d_out.alloc(out_total + 64))) return st;
+            if (st) return SWC_OK;
+            if ((st = d_out.alloc(out_total + 64))) return SWC_OK;
+            { void *scr = nullptr; if (scratch_get(inflate_scratch_bytes(nu, out_total), &scr, stream)) return SWC_OK; }
             m = meta.as<u64>();
             SWC_CUDA_TRY(cudaMemcpyAsync(m, h_inoff.data(), nu * 8, cudaMemcpyHostToDevice, stream));
             SWC_CUDA_TRY(cudaMemcpyAsync(m + nu, h_inlen.data(), nu * 8, cudaMemcpyHostToDevice, stream));
@@ -248,8 +310,8 @@ int gzip_multi_batch(const uint8_t *in, size_t n, const u8 *d_in, HostOut &o, st
         if (accepted) {
             DevBuf gm, d_g;
             int st = gm.alloc(accepted * 24);
-            if (st) return st;
-            if ((st = d_g.alloc(acc_bytes + 16))) return st;
+            if (st) return SWC_OK;
+            if ((st = d_g.alloc(acc_bytes + 16))) return SWC_OK;
             u64 *g = gm.as<u64>();
             SWC_CUDA_TRY(cudaMemcpyAsync(g, g_src.data(), accepted * 8, cudaMemcpyHostToDevice, stream));
             SWC_CUDA_TRY(cudaMemcpyAsync(g + accepted, g_len.data(), accepted * 8, cudaMemcpyHostToDevice, stream));
@@ -260,7 +322,7 @@ int gzip_multi_batch(const uint8_t *in, size_t n, const u8 *d_in, HostOut &o, st
             if (!dst) return SWC_ERR_OUTPUT_OVERFLOW;
             SWC_CUDA_TRY(cudaStreamSynchronize(stream));
             if ((st = copy_pageable(dst, d_g.p, acc_bytes, false))) return st;
-            for (size_t i = 0; i < accepted; i++) ends.push_back(base + g_dst[i] + g_len[i]);
+            for (size_t i = 0; i < accepted; i++) { ends.push_back(base + g_dst[i] + g_len[i]); starts.push_back(cs[i].at); }
             *off = cs[accepted - 1].next;
             if (trace) fprintf(stderr, "[swc] gzip round: %zu accepted, gathered + copied back at %.1f ms\n", accepted, now() - t0);
         }
@@ -269,9 +331,10 @@ int gzip_multi_batch(const uint8_t *in, size_t n, const u8 *d_in, HostOut &o, st
         if (accepted == cs.size()) continue;                             // next round (or done)
         // ---- member idx did not validate: decode it the sequential way, then resynchronise on the candidate list
         bool crc_error = false;
+        const size_t member_at = *off;
         int st = gzip_member(in, n, d_in, off, o, &crc_error);
         if (st) return st;
-        ends.push_back(o.len);
+        ends.push_back(o.len); starts.push_back(member_at);
         if (crc_error) { *result = SWC_GZIP_WRONG_CRC; *stop = true; return SWC_OK; }
         idx = (size_t)(std::lower_bound(pos.begin(), pos.end(), *off) - pos.begin());
     }
@@ -287,6 +350,7 @@ int upload(DevBuf &d, const uint8_t *in, size_t n) {
 template <typename F>
 int host_check(const uint8_t *in, size_t n, F fn) {
     if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    ApiLock api_lock;
     DevBuf d;
     int st = upload(d, in, n);
     if (st) return st;
@@ -302,6 +366,7 @@ int32_t swc_gzip_unarchive(const uint8_t *in, size_t in_len, uint8_t **out, size
     *out = nullptr; *out_len = 0;
     if (consumed_bytes) *consumed_bytes = 0;
     if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    ApiLock api_lock;
     DevBuf d_in;
     int st = upload(d_in, in, in_len);
     if (st) return st;
@@ -313,44 +378,72 @@ int32_t swc_gzip_unarchive(const uint8_t *in, size_t in_len, uint8_t **out, size
     return crc_error ? SWC_GZIP_WRONG_CRC : SWC_OK;
 }
 
-int32_t swc_gzip_multi_unarchive(const uint8_t *in, size_t in_len,
-                                 uint8_t **out, size_t *out_len, size_t **member_ends, size_t *n_members) {
+// GzipArchive.multiUnarchive GzipArchive.swift:52-77
+static int gzip_multi(const uint8_t *in, size_t in_len, uint8_t **out, size_t *out_len, size_t **member_ends, size_t **member_in_off,
+                      size_t *n_members) {
     if (!out || !out_len || !member_ends || !n_members) return SWC_ERR_INVALID_ARG;
     *out = nullptr; *out_len = 0; *member_ends = nullptr; *n_members = 0;
+    if (member_in_off) *member_in_off = nullptr;
     if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    ApiLock api_lock;
     DevBuf d_in;
     int st = upload(d_in, in, in_len);
     if (st) return st;
     HostOut o;
-    std::vector<size_t> ends;
+    std::vector<size_t> ends, starts;
     size_t off = 0;
     int result = SWC_OK;
     bool stop = false;
-    if ((st = gzip_multi_batch(in, in_len, d_in.as<u8>(), o, ends, &off, &result, &stop))) return st;
+    if ((st = gzip_multi_batch(in, in_len, d_in.as<u8>(), o, ends, starts, &off, &result, &stop))) return st;
     while (off < in_len && !stop) {
         bool crc_error = false;
+        const size_t member_at = off;
         if ((st = gzip_member(in, in_len, d_in.as<u8>(), &off, o, &crc_error))) return st;
-        ends.push_back(o.len);
+        ends.push_back(o.len); starts.push_back(member_at);
         if (crc_error) { result = SWC_GZIP_WRONG_CRC; break; }
     }
     if ((st = o.release_to(out, out_len))) return st;
     *member_ends = (size_t *)swc_alloc(sizeof(size_t) * (ends.size() + 1));
     for (size_t i = 0; i < ends.size(); i++) (*member_ends)[i] = ends[i];
+    if (member_in_off) {
+        *member_in_off = (size_t *)swc_alloc(sizeof(size_t) * (starts.size() + 1));
+        for (size_t i = 0; i < starts.size(); i++) (*member_in_off)[i] = starts[i];
+        (*member_in_off)[starts.size()] = off;
+    }
     *n_members = ends.size();
     return result;
+}
+
+int32_t swc_gzip_multi_unarchive(const uint8_t *in, size_t in_len,
+                                 uint8_t **out, size_t *out_len, size_t **member_ends, size_t *n_members) {
+    return gzip_multi(in, in_len, out, out_len, member_ends, nullptr, n_members);
+}
+
+int32_t swc_gzip_multi_unarchive_members(const uint8_t *in, size_t in_len,
+                                         uint8_t **out, size_t *out_len, size_t **member_ends, size_t **member_in_off,
+                                         size_t *n_members) {
+    if (!member_in_off) return SWC_ERR_INVALID_ARG;
+    return gzip_multi(in, in_len, out, out_len, member_ends, member_in_off, n_members);
+}
+
+int32_t swc_gzip_header_parse(const uint8_t *in, size_t in_len, size_t member_off, swc_gzip_header *hdr) {
+    if (!in || !hdr) return SWC_ERR_INVALID_ARG;
+    return gzip_parse(in, in_len, member_off, hdr);
+}
+
+int32_t swc_zlib_header_parse(const uint8_t *in, size_t in_len, swc_zlib_header *hdr) {
+    if (!in || !hdr) return SWC_ERR_INVALID_ARG;
+    return zlib_parse(in, in_len, hdr);
 }
 
 int32_t swc_zlib_unarchive(const uint8_t *in, size_t n, uint8_t **out, size_t *out_len) {
     if (!out || !out_len) return SWC_ERR_INVALID_ARG;
     *out = nullptr; *out_len = 0;
-    if (n < 2) return SWC_ZLIB_WRONG_COMPRESSION_METHOD;             // ZlibHeader.swift:49
-    const unsigned cmf = in[0], flags = in[1];
-    if ((cmf & 0xF) != 8) return SWC_ZLIB_WRONG_COMPRESSION_METHOD;
-    if (((cmf & 0xF0) >> 4) > 7) return SWC_ZLIB_WRONG_COMPRESSION_INFO;
-    if (((cmf << 8) + flags) % 31 != 0) return SWC_ZLIB_WRONG_FCHECK;
-    size_t off = 2;
-    if ((flags & 0x20) >> 5) { if (n - off < 4) return SWC_ZLIB_WRONG_FCHECK; off += 4; }
+    swc_zlib_header zh;
+    { const int hst = zlib_parse(in, n, &zh); if (hst) return hst; }
+    const size_t off = zh.header_len;
     if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    ApiLock api_lock;
     DevBuf d_in;
     int st = upload(d_in, in, n);
     if (st) return st;
@@ -369,6 +462,21 @@ int32_t swc_zlib_unarchive(const uint8_t *in, size_t n, uint8_t **out, size_t *o
     }
     if ((st = to_host_alloc(r.out.p, r.out_len, out, out_len))) return st;
     return result;
+}
+
+int32_t swc_crc32_batch(const uint8_t *in_base, const uint64_t *off, const uint64_t *len, const int32_t *status,
+                        uint32_t *result, uint64_t n, void *cuda_stream) {
+    if (n == 0) return SWC_OK;
+    if (!in_base || !off || !len || !result) return SWC_ERR_INVALID_ARG;
+    if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    return checks::crc32_units(in_base, off, len, status, result, n, (cudaStream_t)cuda_stream);
+}
+int32_t swc_xxh32_batch(const uint8_t *in_base, const uint64_t *off, const uint64_t *len,
+                        uint32_t *result, uint64_t n, void *cuda_stream) {
+    if (n == 0) return SWC_OK;
+    if (!in_base || !off || !len || !result) return SWC_ERR_INVALID_ARG;
+    if (ensure_device()) return SWC_ERR_NO_DEVICE;
+    return checks::xxh32_batch(in_base, off, len, result, n, (cudaStream_t)cuda_stream);
 }
 
 int32_t swc_crc32(const uint8_t *in, size_t n, uint32_t *result) {

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include "common.cuh"
 #include "bzip2.cuh"
+#include "host_util.h"
 
 namespace swc {
 namespace bzip2 {
@@ -574,8 +575,6 @@ done:
     }
 }
 
-static bool g_crc_ready = false;
-
 size_t scratch_per_unit(u64 cap) {
     const u64 scr_cap = (cap + 3) & ~3ull;
     // bwt | succ (u32) | selectors | text
@@ -584,12 +583,13 @@ size_t scratch_per_unit(u64 cap) {
 
 int launch(const Args &a, cudaStream_t stream) {
     if (a.n == 0) return SWC_OK;
-    if (!g_crc_ready) {
+    int st = configure_once(CFG_BZIP2_CRC, [](DeviceCtx &) {          // __constant__ memory is per device
         u32 tab[256];
         for (u32 i = 0; i < 256; i++) { u32 c = i << 24; for (int k = 0; k < 8; k++) c = (c & 0x80000000u) ? (c << 1) ^ 0x04C11DB7u : c << 1; tab[i] = c; }
         SWC_CUDA_TRY(cudaMemcpyToSymbol(c_bzcrc, tab, sizeof(tab)));
-        g_crc_ready = true;
-    }
+        return (int)SWC_OK;
+    });
+    if (st) return st;
     bzip2_kernel<<<(unsigned)((a.n + WARPS - 1) / WARPS), WARPS * 32, 0, stream>>>(a);
     count_launch();
     SWC_CUDA_TRY(cudaGetLastError());

@@ -6,9 +6,47 @@
 #include <vector>
 #include "common.cuh"
 
+#include <mutex>
+
 namespace swc {
 
 int ensure_device();
+
+// ---- per-device library context (runtime.cu) -----------------------------------------------------------------------------
+// The reference is re-entrant; here the mutable state is one lazily created context per device: scratch arenas, the streams /
+// pinned result buffer of the *_batch_host paths, one-time kernel configuration flags.  Every C-ABI entry point that touches it
+// holds the device's API mutex for the duration of the call (ApiLock), so any number of host threads may call into the library
+// concurrently on the same or on different devices; calls on one device are serialised, calls on different devices are not.
+struct DeviceCtx {
+    std::recursive_mutex api_mu;
+    std::mutex cfg_mu;
+    bool configured[16] = {};
+    cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t tables_ready = nullptr;
+    uint8_t *h_res = nullptr;
+    size_t h_res_bytes = 0;
+    int num_sms = 0;
+};
+DeviceCtx &device_ctx();                 // context of the CURRENT device
+struct ApiLock {
+    std::unique_lock<std::recursive_mutex> lk;
+    ApiLock() : lk(device_ctx().api_mu) {}
+};
+enum { CFG_INFLATE_K1 = 0, CFG_INFLATE_K1W = 1, CFG_INFLATE_K1L = 2, CFG_LZMA = 3, CFG_BZIP2_CRC = 4, CFG_LZ4 = 5 };
+// runs `f` (returning an swc status) once per device, thread-safe; a failing `f` is retried by the next caller
+template <typename F> int configure_once(int slot, F f) {
+    DeviceCtx &c = device_ctx();
+    std::lock_guard<std::mutex> g(c.cfg_mu);
+    if (c.configured[slot]) return SWC_OK;
+    if (!c.num_sms) {
+        int dev = 0;
+        SWC_CUDA_TRY(cudaGetDevice(&dev));
+        SWC_CUDA_TRY(cudaDeviceGetAttribute(&c.num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int st = f(c);
+    if (st == SWC_OK) c.configured[slot] = true;
+    return st;
+}
 
 // RAII device allocation (single-unit paths; the batch paths use caller memory + the scratch pool)
 struct DevBuf {

@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include "common.cuh"
 #include "inflate.cuh"
+#include "host_util.h"
 
 namespace swc {
 namespace inflate {
@@ -565,8 +566,7 @@ int launch(const BatchArgs &a, cudaStream_t stream) {
     //   small batches (and the single-stream API calls) cannot fill the chip with one lane per stream, so they take the
     //                   warp-per-unit decoder K1w (32 lanes on every stream, ~10 x lower latency per stream) + K2.
     //   SWC_DEFLATE_K1 = lut | warp | thread forces K1L / K1w / the round-1 limit-compare K1 (kept for A/B runs).
-    static int forced = -2;
-    if (forced == -2) { const char *e = getenv("SWC_DEFLATE_K1"); forced = !e ? -1 : (e[0] == 'w' ? 1 : (e[0] == 't' ? 2 : 0)); }
+    static const int forced = [] { const char *e = getenv("SWC_DEFLATE_K1"); return !e ? -1 : (e[0] == 'w' ? 1 : (e[0] == 't' ? 2 : 0)); }();
     const int path = forced >= 0 ? forced : (a.n < 20000 ? 1 : 0);
     SWC_CUDA_TRY(cudaMemsetAsync(a.ticket, 0, 16, stream));
     timing_mark(stream);
@@ -577,18 +577,14 @@ int launch(const BatchArgs &a, cudaStream_t stream) {
         int st = launch_warp(a, stream);
         if (st) return st;
     } else {
-        int dev = 0;
-        SWC_CUDA_TRY(cudaGetDevice(&dev));
-        static bool configured[64] = {};
-        static int num_sms[64] = {};
-        if (!configured[dev & 63]) {
+        int st = configure_once(CFG_INFLATE_K1, [](DeviceCtx &) {
             SWC_CUDA_TRY(cudaFuncSetAttribute(inflate_huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-            SWC_CUDA_TRY(cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
-            configured[dev & 63] = true;
-        }
+            return (int)SWC_OK;
+        });
+        if (st) return st;
         const u64 per_cta = WARPS_PER_CTA * 32;
         u64 g1 = (a.n + per_cta - 1) / per_cta;
-        const u64 resident = (u64)num_sms[dev & 63] * CTAS_PER_SM;          // persistent lanes: one CTA per resident slot
+        const u64 resident = (u64)device_ctx().num_sms * CTAS_PER_SM;       // persistent lanes: one CTA per resident slot
         if (g1 > resident) g1 = resident;
         inflate_huffman_kernel<<<(unsigned)g1, WARPS_PER_CTA * 32, SMEM_BYTES, stream>>>(a);
         count_launch();

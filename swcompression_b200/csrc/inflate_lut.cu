@@ -23,6 +23,7 @@
 // Variants that fused the LZ77 copy into this kernel were measured slower: profiles/r2_experiments.md.
 #include "common.cuh"
 #include "inflate.cuh"
+#include "host_util.h"
 
 namespace swc {
 namespace inflate {
@@ -615,18 +616,14 @@ inflate_lut_kernel(BatchArgs a) {
 }  // namespace k1l
 
 int launch_lut(const BatchArgs &a, cudaStream_t stream) {
-    int dev = 0;
-    SWC_CUDA_TRY(cudaGetDevice(&dev));
-    static bool configured[64] = {};
-    static int num_sms[64] = {};
-    if (!configured[dev & 63]) {
+    int st = configure_once(CFG_INFLATE_K1L, [](DeviceCtx &) {
         SWC_CUDA_TRY(cudaFuncSetAttribute(k1l::inflate_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1l::SMEM_BYTES));
-        SWC_CUDA_TRY(cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
-        configured[dev & 63] = true;
-    }
+        return (int)SWC_OK;
+    });
+    if (st) return st;
     const u64 per_cta = k1l::WARPS_PER_CTA * 32;
     u64 grid = (a.n + per_cta - 1) / per_cta;
-    const u64 resident = (u64)num_sms[dev & 63] * k1l::CTAS_PER_SM;          // persistent lanes: one CTA per resident slot
+    const u64 resident = (u64)device_ctx().num_sms * k1l::CTAS_PER_SM;       // persistent lanes: one CTA per resident slot
     if (grid > resident) grid = resident;
     k1l::inflate_lut_kernel<<<(unsigned)grid, k1l::WARPS_PER_CTA * 32, k1l::SMEM_BYTES, stream>>>(a);
     count_launch();

@@ -15,6 +15,7 @@
 // Code sets with Kraft sum > 1 are routed to inflate_slow_kernel exactly like in K1.
 #include "common.cuh"
 #include "inflate.cuh"
+#include "host_util.h"
 
 namespace swc {
 namespace inflate {
@@ -576,22 +577,20 @@ inflate_warp_kernel(BatchArgs a) {
 }
 
 int launch_warp(const BatchArgs &a, cudaStream_t stream) {
-    // per-device launch configuration (a process may drive several devices: swc_set_device / torch.cuda.set_device)
-    static bool configured[64] = {};
-    static int resident_ctas[64] = {};
     const size_t smem = sizeof(Smem) * WARPS;
+    static int per_sm_cached[64] = {};
     int dev = 0;
     SWC_CUDA_TRY(cudaGetDevice(&dev));
-    if (!configured[dev & 63]) {
-        int num_sms = 0, per_sm = 1;
-        SWC_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    int st = configure_once(CFG_INFLATE_K1W, [&](DeviceCtx &) {
+        int per_sm = 1;
         SWC_CUDA_TRY(cudaFuncSetAttribute(inflate_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SWC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, inflate_warp_kernel, WARPS * 32, smem));
-        resident_ctas[dev & 63] = num_sms * (per_sm < 1 ? 1 : per_sm);
-        configured[dev & 63] = true;
-    }
+        per_sm_cached[dev & 63] = per_sm < 1 ? 1 : per_sm;
+        return (int)SWC_OK;
+    });
+    if (st) return st;
     u64 grid = (a.n + WARPS - 1) / WARPS;
-    const u64 resident = (u64)resident_ctas[dev & 63];
+    const u64 resident = (u64)device_ctx().num_sms * per_sm_cached[dev & 63];
     if (grid > resident) grid = resident;
     inflate_warp_kernel<<<(unsigned)grid, WARPS * 32, smem, stream>>>(a);
     count_launch();

@@ -9,6 +9,7 @@
 // copies done by all lanes.  The output buffer doubles as the dictionary (the reference never wraps it either).
 #include "common.cuh"
 #include "lzma.cuh"
+#include "host_util.h"
 
 namespace swc {
 namespace lzma {
@@ -350,11 +351,11 @@ __global__ void __launch_bounds__(WARPS * 32) lzma_kernel(Args a) {
 
 int launch(const Args &a, cudaStream_t stream) {
     if (a.n == 0) return SWC_OK;
-    static bool configured = false;
-    if (!configured) {
+    int st = configure_once(CFG_LZMA, [](DeviceCtx &) {
         SWC_CUDA_TRY(cudaFuncSetAttribute(lzma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        configured = true;
-    }
+        return (int)SWC_OK;
+    });
+    if (st) return st;
     lzma_kernel<<<(unsigned)((a.n + WARPS - 1) / WARPS), WARPS * 32, SMEM_BYTES, stream>>>(a);
     count_launch();
     SWC_CUDA_TRY(cudaGetLastError());

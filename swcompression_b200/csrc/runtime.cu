@@ -25,6 +25,13 @@ int cuda_fail(cudaError_t e, const char *where) {
     return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? SWC_ERR_NO_DEVICE : SWC_ERR_CUDA;
 }
 
+static DeviceCtx g_ctx[64];
+DeviceCtx &device_ctx() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    return g_ctx[dev & 63];
+}
+
 // ---- grow-only scratch pool, one per device ----
 struct Pool { void *p = nullptr; size_t bytes = 0; };
 static std::mutex g_pool_mu;

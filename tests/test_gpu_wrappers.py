@@ -54,7 +54,7 @@ def test_gzip_zlib_roundtrip_errors_and_payloads(gpu, oracle):
     assert gpu.GzipArchive.unarchive(gzip.compress(raw)) == raw
     assert gpu.ZlibArchive.unarchive(zlib.compress(raw)) == raw
     a, b = H.textlike(5000, 22), H.textlike(70000, 23)
-    assert gpu.GzipArchive.multiUnarchive(gzip.compress(a) + gzip.compress(b)) == [a, b]
+    assert [m.data for m in gpu.GzipArchive.multiUnarchive(gzip.compress(a) + gzip.compress(b))] == [a, b]
     g = bytearray(gzip.compress(raw)); g[-8] ^= 1
     with pytest.raises(gpu.GzipError) as e:
         gpu.GzipArchive.unarchive(bytes(g))
@@ -102,7 +102,7 @@ def test_gzip_multi_member_batch_matches_oracle(gpu, oracle):
     data = b"".join(blobs)
     ost, oparts, _ = oracle.gzip_multi_unarchive(data)
     assert ost == 0 and oparts == raws
-    assert gpu.GzipArchive.multiUnarchive(data) == raws
+    assert [m.data for m in gpu.GzipArchive.multiUnarchive(data)] == raws
     # wrong CRC in member 17: members 0..17 are returned with the error
     bad = list(blobs)
     b = bytearray(bad[17]); b[-8] ^= 0x40; bad[17] = bytes(b)
@@ -110,7 +110,7 @@ def test_gzip_multi_member_batch_matches_oracle(gpu, oracle):
     ost, oparts, _ = oracle.gzip_multi_unarchive(data)
     with pytest.raises(gpu.GzipError) as e:
         gpu.GzipArchive.multiUnarchive(data)
-    assert e.value.code == ost and e.value.case == "wrongCRC" and e.value.payload == oparts == raws[:18]
+    assert e.value.code == ost and e.value.case == "wrongCRC" and [m.data for m in e.value.payload] == oparts == raws[:18]
     # wrong ISIZE in member 30, damaged payload in member 5, trailing garbage, truncation: same error as the oracle
     variants = []
     b = bytearray(blobs[30]); b[-1] ^= 1
@@ -123,7 +123,7 @@ def test_gzip_multi_member_batch_matches_oracle(gpu, oracle):
     for v in variants:
         ost, oparts, _ = oracle.gzip_multi_unarchive(v)
         if ost == 0:
-            assert gpu.GzipArchive.multiUnarchive(v) == oparts
+            assert [m.data for m in gpu.GzipArchive.multiUnarchive(v)] == oparts
         else:
             with pytest.raises(gpu.SWCompressionError) as e:
                 gpu.GzipArchive.multiUnarchive(v)
@@ -133,4 +133,36 @@ def test_gzip_multi_member_batch_matches_oracle(gpu, oracle):
     praw = [gzip.decompress(p) for p in pool]
     order = [rng.randrange(24) for _ in range(3000)]
     got = gpu.GzipArchive.multiUnarchive(b"".join(pool[i] for i in order))
-    assert len(got) == 3000 and all(got[j] == praw[order[j]] for j in range(3000))
+    assert len(got) == 3000 and all(got[j].data == praw[order[j]] for j in range(3000))
+
+
+def test_gzip_members_carry_their_headers(gpu):
+    """GzipArchive.multiUnarchive -> [Member] (GzipArchive.swift:13-22,52-77): every member comes with the GzipHeader parsed at
+    its own offset inside the archive — sequential walk (few members) and batched walk (many members) alike."""
+    import io
+    def member(raw, name, mtime, comment=None):
+        bio = io.BytesIO()
+        with gzip.GzipFile(filename=name, mode="wb", fileobj=bio, mtime=mtime) as f:
+            f.write(raw)
+        blob = bytearray(bio.getvalue())
+        if comment is not None:                  # add FCOMMENT by hand (python's gzip never writes one)
+            assert blob[3] == 0x08
+            name_end = blob.index(0, 10) + 1
+            blob[3] |= 0x10
+            blob[name_end:name_end] = comment.encode("latin-1") + b"\0"
+        return bytes(blob)
+    for count in (3, 40):
+        raws = [H.textlike(300 + 17 * i, 4000 + i) for i in range(count)]
+        blobs = [member(raws[i], f"file_{i}.txt", 1500000000 + i, comment=(f"c{i}" if i % 3 == 0 else None)) for i in range(count)]
+        ms = gpu.GzipArchive.multiUnarchive(b"".join(blobs))
+        assert [m.data for m in ms] == raws
+        for i, m in enumerate(ms):
+            assert m.header.fileName == f"file_{i}.txt" and m.header.compressionMethod == "deflate"
+            assert int(m.header.modificationTime.timestamp()) == 1500000000 + i
+            assert m.header.comment == (f"c{i}" if i % 3 == 0 else None)
+            assert m.header.extraFields == []
+    h = gpu.GzipHeader(H.fixture("GZip/test1.gz"))               # GzipTests.swift header checks: name + mtime of test1.gz
+    assert h.fileName == "test1.answer" and int(h.modificationTime.timestamp()) == 1482698300 and h.osType == "unix"
+    assert not h.isTextFile and h.comment is None
+    z = gpu.ZlibHeader(zlib.compress(b"abc", 9))
+    assert z.windowSize == 32768 and z.compressionLevel == "slowAlgorithm" and z.compressionMethod == "deflate"

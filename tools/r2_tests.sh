@@ -1,0 +1,2 @@
+cd /root/repo
+python -m pytest tests -m gpu -x -q 2>&1 | tail -15

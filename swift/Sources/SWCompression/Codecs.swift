@@ -108,10 +108,84 @@ public class GzipArchive: Archive {                                  // Sources/
     public static func unarchive(archive data: Data) throws -> Data {
         try single(data) { p, n, o, ol in var used = 0; return swc_gzip_unarchive(p, n, o, ol, &used) }
     }
-    /// The reference returns `[Member]` (header + data); header parsing is metadata and stays in Swift
-    /// (GzipHeader.swift is unchanged and can be re-used on `archive` with the member offsets).
-    public static func multiUnarchiveData(archive data: Data) throws -> [Data] {
-        try multi(data) { p, n, o, ol, e, c in swc_gzip_multi_unarchive(p, n, o, ol, e, c) }
+    /// Represents the member of a multi-member GZip archive (GzipArchive.swift:13-22).
+    public struct Member: Sendable {
+        public let header: GzipHeader
+        public let data: Data
+        let crcError: Bool
+    }
+    /// GzipArchive.swift:52-77.  The engine returns the decoded bytes, the end of every member inside them and the offset of
+    /// every member inside `archive`; each Member.header is parsed at its offset with swc_gzip_header_parse.
+    public static func multiUnarchive(archive data: Data) throws -> [Member] {
+        var out: UnsafeMutablePointer<UInt8>? = nil, outLen = 0
+        var ends: UnsafeMutablePointer<Int>? = nil, offs: UnsafeMutablePointer<Int>? = nil, count = 0
+        let st = data.withUnsafeBytes { raw in
+            swc_gzip_multi_unarchive_members(raw.bindMemory(to: UInt8.self).baseAddress, raw.count, &out, &outLen, &ends, &offs, &count)
+        }
+        defer { swc_free(out); swc_free(ends); swc_free(offs) }
+        var members = [Member](), prev = 0
+        for i in 0..<count {
+            let header = try GzipHeader(archive: data, memberOffset: offs![i])
+            let failing = st == 605 && i == count - 1
+            members.append(Member(header: header, data: Data(bytes: out! + prev, count: ends![i] - prev), crcError: failing))
+            prev = ends![i]
+        }
+        if st == 605 { throw GzipError.wrongCRC(members) }                              // SWC_GZIP_WRONG_CRC; GzipArchive.swift:73-75
+        guard st == 0 else { throw swcError(st) }
+        return members
+    }
+}
+
+/// Sources/GZip/GzipHeader.swift:10-60 — same stored properties; `init(archive:)` goes through swc_gzip_header_parse.
+public struct GzipHeader: Sendable {
+    public var compressionMethod: CompressionMethod
+    public var modificationTime: Date?
+    public var osType: FileSystemType
+    public var fileName: String?
+    public var comment: String?
+    public var isTextFile: Bool
+    public var extraFields: [ExtraField]
+
+    public init(archive data: Data) throws { try self.init(archive: data, memberOffset: 0) }
+
+    init(archive data: Data, memberOffset: Int) throws {
+        var h = swc_gzip_header()
+        let st = data.withUnsafeBytes { raw in
+            swc_gzip_header_parse(raw.bindMemory(to: UInt8.self).baseAddress, raw.count, memberOffset, &h)
+        }
+        guard st == 0 else { throw swcError(st) }
+        let base = data.startIndex
+        func field(_ off: Int, _ len: Int) -> Data { data[(base + off)..<(base + off + len)] }
+        compressionMethod = .deflate
+        modificationTime = h.modification_time == 0 ? nil : Date(timeIntervalSince1970: TimeInterval(h.modification_time))
+        osType = FileSystemType(h.os_type)
+        fileName = h.has_file_name != 0 ? String(data: field(h.file_name_off, h.file_name_len), encoding: .isoLatin1) : nil
+        comment = h.has_comment != 0 ? String(data: field(h.comment_off, h.comment_len), encoding: .isoLatin1) : nil
+        isTextFile = h.is_text_file != 0
+        extraFields = []
+        var p = h.extra_off
+        let end = h.extra_off + h.extra_len
+        while p < end {
+            let len = Int(data[base + p + 2]) | Int(data[base + p + 3]) << 8
+            extraFields.append(ExtraField(data[base + p], data[base + p + 1], [UInt8](field(p + 4, len))))
+            p += 4 + len
+        }
+    }
+}
+
+/// Sources/Zlib/ZlibHeader.swift:10-45
+public struct ZlibHeader: Sendable {
+    public enum CompressionLevel: Int, Sendable { case fastestAlgorithm = 0, fastAlgorithm, defaultAlgorithm, slowAlgorithm }
+    public let compressionMethod: CompressionMethod = .deflate
+    public let compressionLevel: CompressionLevel
+    public let windowSize: Int
+
+    public init(archive data: Data) throws {
+        var h = swc_zlib_header()
+        let st = data.withUnsafeBytes { raw in swc_zlib_header_parse(raw.bindMemory(to: UInt8.self).baseAddress, raw.count, &h) }
+        guard st == 0 else { throw swcError(st) }
+        compressionLevel = CompressionLevel(rawValue: Int(h.compression_level))!
+        windowSize = Int(h.window_size)
     }
 }
 

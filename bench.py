@@ -10,7 +10,7 @@ GPU; 4096 distinct synthetic units tiled x64 on the device to bound host prep ti
 compressed batch resident in HBM; `e2e` goes through swc_deflate_decompress_batch_host with pinned HOST buffers, i.e.
 host->device and device->host copies inside the timed region (the same 262 144 units).
 Multi-GPU: units are independent, every rank decodes its own shard with no data-path collective (weak scaling);
-NCCL is used for the barrier and the max-over-ranks time only.
+rank 0 owns the unit list and scatters byte-balanced shards over NCCL; `multi_gpu.legs` adds the gather / all-gather variants.
 """
 import argparse
 import ctypes as C
@@ -125,6 +125,34 @@ def cpu_decode_throughput(units, seconds_budget, threads):
     return nbytes / sec / 1e9, total, sec
 
 
+def cgroup_cpu_limit():
+    """CPUs the container may actually use (cgroup v2 cpu.max / v1 cfs quota), or None when unlimited / unknown."""
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        return None if q == "max" else float(q) / float(per)
+    except Exception:
+        pass
+    try:
+        q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        return None if q <= 0 else q / per
+    except Exception:
+        return None
+
+
+def best_thread_count(units):
+    """The box shows 128 logical CPUs but may schedule far fewer for this container (measured: linear to 16 threads, flat at
+    32, slower at 128).  "All the host threads it can use" = the count with the highest measured throughput."""
+    ncpu = os.cpu_count() or 1
+    cands = sorted({max(1, ncpu >> k) for k in range(0, 5)} | {min(ncpu, 16), min(ncpu, 24), min(ncpu, 48)})
+    sweep = {}
+    for th in cands:
+        v, _, _ = cpu_decode_throughput(units, 1.5, th)
+        sweep[th] = v
+    best = max(sweep, key=sweep.get)
+    return best, {str(k): round(v, 4) for k, v in sweep.items()}
+
+
 def physical_cores():
     try:
         pairs = set()
@@ -149,9 +177,8 @@ def run_reference(args):
         return 0
     n_units = (args.units // min(args.distinct, args.units)) * min(args.distinct, args.units)
     units, _ = make_corpus(256)
-    threads = os.cpu_count() or 1
+    threads, sweep = best_thread_count(units)
     per_step = 6.0
-    cpu_decode_throughput(units, 1.0, threads)   # warm
     vals, n_total = [], 0
     for _ in range(args.steps):
         v, n, dt = cpu_decode_throughput(units, per_step, threads)
@@ -162,7 +189,8 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "config": workload_config(n_units, min(args.distinct, n_units), args.gpus),
-        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": threads, "physical_cores": physical_cores(), "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": threads, "logical_cpus": os.cpu_count(), "physical_cores": physical_cores(),
+                         "cgroup_cpu_limit": cgroup_cpu_limit(), "thread_sweep_GBps": sweep, "kind": "port",
                          "sample": f"{n_total} units of 64 KiB (256 distinct, same generator/compressor as the GPU workload) in "
                                    f"{args.steps} steps of ~{per_step:.0f} s on {threads} pthreads (oracle/batch_mt.c)",
                          "note": "the Swift reference cannot be built here (no Swift toolchain); this arm times the C restatement of "
@@ -184,11 +212,14 @@ def run_product(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    from swcompression_b200 import shard
     n_units = args.units
     distinct = min(args.distinct, n_units)
     tile = n_units // distinct
     n_units = tile * distinct
-    units, crcs = make_corpus(distinct, seed0=2 + 100000 * rank, world=world)      # fork the generator pool BEFORE CUDA is initialised
+    nominal_units = n_units
+    # Rank 0 owns the unit list: it builds the corpus, the other ranks receive their shard over NCCL.
+    units, crcs = make_corpus(distinct, seed0=2) if rank == 0 else (None, None)      # fork the generator pool BEFORE CUDA is initialised
     assert torch.cuda.is_available(), "bench.py product arm needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
@@ -198,46 +229,67 @@ def run_product(args):
     L = _lib.lib()
     L.swc_timing_collect.argtypes = [C.c_void_p, C.c_int32]
 
-    buf, offs, lens = pack_units(units)
-    in_bytes_distinct = int(lens.sum())
-    stride = len(buf) - 64
-    # tile the compressed corpus on the device: unit j of tile t lives at offs[j] + t * stride
-    d_one = torch.from_numpy(buf[:stride]).to(dev)
-    d_in = d_one.repeat(tile)
-    d_in = torch.cat([d_in, torch.zeros(64, dtype=torch.uint8, device=dev)])
-    all_off = (offs[None, :] + (np.arange(tile, dtype=np.uint64) * np.uint64(stride))[:, None]).reshape(-1)
-    all_len = np.tile(lens, tile)
-    b = Batch.__new__(Batch)
-    Batch.__init__(b, "deflate", np.zeros(1, dtype=np.uint8), all_off, all_len, UNIT, device=str(dev))
-    b.d_in = d_in
-    total_in = in_bytes_distinct * tile
-    total_out = n_units * UNIT
-    torch.cuda.synchronize(dev)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    scatter_ms = 0.0
+    if rank == 0:
+        buf, offs, lens = pack_units(units)                   # 16-byte aligned unit starts: stride[i] = padded length
+        strides = np.diff(np.concatenate([offs, [len(buf) - 64]])).astype(np.int64)
+        d_one = torch.from_numpy(buf[:len(buf) - 64]).to(dev)
+    if world == 1:
+        d_in = torch.cat([d_one.repeat(tile), torch.zeros(64, dtype=torch.uint8, device=dev)])
+        l_stride, l_len, begin = np.tile(strides, tile), np.tile(lens.astype(np.int64), tile), 0
+        crc_t = torch.tensor(crcs, dtype=torch.int64, device=dev)
+    else:
+        # the whole job = world x n_units units, tiled from the distinct corpus on rank 0's GPU; byte-balanced contiguous
+        # shards go out with one table broadcast + one NCCL send per rank (timed: scatter_ms)
+        crc_t = torch.zeros(distinct, dtype=torch.int64, device=dev)
+        g_buf = g_stride = g_len = None
+        if rank == 0:
+            crc_t = torch.tensor(crcs, dtype=torch.int64, device=dev)
+            g_buf = d_one.repeat(tile * world)
+            g_stride, g_len = np.tile(strides, tile * world), np.tile(lens.astype(np.int64), tile * world)
+        dist.broadcast(crc_t, src=0)
+        barrier()
+        t0 = time.perf_counter()
+        d_loc, l_stride, l_cap, (begin, end), l_len = shard.scatter_units(g_buf, g_stride, None if g_stride is None else np.full(len(g_stride), UNIT), dev, extra=g_len)
+        barrier()
+        scatter_ms = (time.perf_counter() - t0) * 1e3
+        del g_buf
+        d_in = torch.cat([d_loc, torch.zeros(64, dtype=torch.uint8, device=dev)])
+        n_units = end - begin
+    all_off = np.concatenate([[0], np.cumsum(l_stride)[:-1]]).astype(np.uint64)
+    all_len = l_len.astype(np.uint64)
+    b = Batch.__new__(Batch)
+    Batch.__init__(b, "deflate", np.zeros(1, dtype=np.uint8), all_off, all_len, UNIT, device=str(dev))
+    b.d_in = d_in
+    total_in = int(all_len.sum())
+    total_out = n_units * UNIT
+    torch.cuda.synchronize(dev)
+
     for _ in range(args.warmup):
         b.run()
     barrier()
-    # parity check of the workload itself (outside the timed region): EVERY distinct unit against the CRC-32 of the raw bytes
-    # it was compressed from, every tiled copy against the first copy on the device, a sample against the oracle byte by byte
+    # parity check of the workload itself (outside the timed region): the CRC-32 of EVERY decoded unit (device-side, batched
+    # swc_crc32_batch) against the CRC-32 of the raw bytes it was compressed from; a sample against the oracle byte by byte
     st, ln, used = b.results()
     assert (st == 0).all() and (ln == UNIT).all(), "decode failed"
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import swco
-    tiles = b.d_out[: n_units * UNIT].view(tile, distinct * UNIT)
-    for k in range(1, tile):
-        assert torch.equal(tiles[k], tiles[0]), f"tile {k} differs from tile 0"
-    host_out = tiles[0].cpu().numpy()
-    for i in range(distinct):
-        assert zlib.crc32(host_out[i * UNIT:(i + 1) * UNIT].tobytes()) == crcs[i], f"unit {i}: wrong bytes"
-    assert (used.reshape(tile, distinct) == used[:distinct][None, :]).all()
-    for i in range(0, distinct, max(distinct // 16, 1)):
-        ost, oout, oused = swco.deflate_decompress(units[i])
-        assert ost == 0 and host_out[i * UNIT:(i + 1) * UNIT].tobytes() == oout and used[i] == oused, "parity vs oracle failed"
+    d_crc = torch.zeros(n_units, dtype=torch.int32, device=dev)
+    pp = lambda t: C.c_void_p(t.data_ptr())
+    assert L.swc_crc32_batch(pp(b.d_out), pp(b.d_out_off), pp(b.d_out_len), pp(b.d_status), pp(d_crc), n_units,
+                             C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)) == 0
+    want = crc_t[(torch.arange(n_units, device=dev) + begin) % distinct]
+    assert torch.equal(d_crc.to(torch.int64) & 0xFFFFFFFF, want), "a decoded unit has the wrong CRC-32"
+    if rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import swco
+        host_out = b.d_out[: distinct * UNIT].cpu().numpy()
+        for i in range(0, distinct, max(distinct // 16, 1)):
+            ost, oout, oused = swco.deflate_decompress(units[i])
+            assert ost == 0 and host_out[i * UNIT:(i + 1) * UNIT].tobytes() == oout and used[i] == oused, "parity vs oracle failed"
 
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = L.swc_kernel_launches()
@@ -260,7 +312,43 @@ def run_product(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     ms_per_step = ms_max / args.steps
-    value = total_out * world / (ms_per_step * 1e-3) / 1e9
+    job = torch.tensor([total_out, total_in], dtype=torch.float64, device=dev)     # whole job = the units ALL ranks decoded
+    if world > 1:
+        dist.all_reduce(job, op=dist.ReduceOp.SUM)
+    value = float(job[0].item()) / (ms_per_step * 1e-3) / 1e9
+
+    # ---- SURVEY §8e legs: decode-only / + gather to rank 0 / + all-gather, on a sub-batch whose gathered size fits every GPU ----
+    legs = None
+    if world > 1 and not args.no_legs:
+        n_leg = min(n_units, args.leg_units)
+        lb = Batch.__new__(Batch)
+        Batch.__init__(lb, "deflate", np.zeros(1, dtype=np.uint8), all_off[:n_leg], all_len[:n_leg], UNIT, device=str(dev))
+        lb.d_in = d_in
+        leg_bytes = torch.tensor([n_leg * UNIT], dtype=torch.float64, device=dev)
+        dist.all_reduce(leg_bytes, op=dist.ReduceOp.SUM)
+
+        def timed(fn, reps=3):
+            fn(); barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            barrier()
+            tt = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(leg_bytes.item()) / (float(tt.item()) * 1e-3) / 1e9, float(tt.item())
+
+        out_view = lambda: lb.d_out[: n_leg * UNIT]
+        g0, t_0 = timed(lambda: lb.run())
+        g1, t_1 = timed(lambda: (lb.run(), shard.gather_to_root(out_view())))
+        g2, t_2 = timed(lambda: (lb.run(), shard.allgather(out_view())))
+        legs = {"units_per_gpu": int(n_leg), "decode_only_GBps": g0, "decode_gather_to_root_GBps": g1, "decode_allgather_GBps": g2,
+                "ms": {"decode_only": t_0, "decode_gather_to_root": t_1, "decode_allgather": t_2},
+                "note": "whole-job decompressed GB/s over all ranks; gathers move decoded bytes over NCCL/NVLink (gather: grouped "
+                        "send/recv to rank 0, all-gather: ncclAllGather); sub-batch sized so that world x shard fits one GPU"}
+        del lb
+
 
     # per-kernel durations: 4 marks per step -> intervals [K1L table-lookup decode, slow path (no-op here), K2 record replay, gap]
     iv = np.array(list(tbuf)[:nint], dtype=np.float64)
@@ -293,17 +381,14 @@ def run_product(args):
     e2e = None
     if not args.no_e2e:
         n_e = min(args.e2e_units, n_units)
-        n_e = (n_e // distinct) * distinct if n_e >= distinct else n_e
-        tile_e = max(n_e // distinct, 1)
-        n_e = min(tile_e * distinct, n_units)
-        in_total = stride * tile_e + 64
+        in_total = int(all_off[n_e - 1] + l_stride[n_e - 1]) + 64
         out_total = n_e * UNIT
         p_in = L.swc_alloc_pinned(in_total)
         p_out = L.swc_alloc_pinned(out_total)
         assert p_in and p_out, "pinned allocation failed"
-        h_in = np.ctypeslib.as_array(C.cast(p_in, C.POINTER(C.c_uint8)), shape=(in_total,))
-        for k in range(tile_e):
-            h_in[k * stride:(k + 1) * stride] = buf[:stride]
+        h_in = torch.from_numpy(np.ctypeslib.as_array(C.cast(p_in, C.POINTER(C.c_uint8)), shape=(in_total,)))
+        h_in[: in_total - 64].copy_(d_in[: in_total - 64])            # the same compressed bytes, now in pinned HOST memory
+        torch.cuda.synchronize(dev)
         e_off = np.ascontiguousarray(all_off[:n_e]); e_len = np.ascontiguousarray(all_len[:n_e])
         o_off = (np.arange(n_e, dtype=np.uint64) * np.uint64(UNIT)); o_cap = np.full(n_e, UNIT, dtype=np.uint64)
         r_len = np.zeros(n_e, dtype=np.uint64); r_used = np.zeros(n_e, dtype=np.uint64); r_st = np.zeros(n_e, dtype=np.int32)
@@ -333,10 +418,11 @@ def run_product(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
-        v1, n1, dt1 = cpu_decode_throughput(units[:256], 5.0, 1)
+        cores, sweep = best_thread_count(units[:256])
+        v1, n1, dt1 = cpu_decode_throughput(units[:256], 4.0, 1)
         vN, nN, dtN = cpu_decode_throughput(units[:256], 10.0, cores)
-        cpu = {"value": vN, "unit": "GB/s", "cores": cores, "physical_cores": physical_cores(), "kind": "port",
+        cpu = {"value": vN, "unit": "GB/s", "cores": cores, "logical_cpus": os.cpu_count(), "physical_cores": physical_cores(),
+               "cgroup_cpu_limit": cgroup_cpu_limit(), "thread_sweep_GBps": sweep, "kind": "port",
                "sample": f"{nN} units of 64 KiB (same generator/compressor as the GPU workload) in {dtN:.1f} s on {cores} pthreads "
                          f"(oracle/batch_mt.c, no interpreter in the loop)",
                "single_thread_value": v1, "thread_scaling": vN / v1 if v1 else None,
@@ -347,9 +433,12 @@ def run_product(args):
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": workload_config(n_units, distinct, world),
-            "compressed_bytes_per_gpu": total_in,
+            "config": workload_config(nominal_units, distinct, world),
+            "compressed_bytes_per_gpu": total_in, "units_this_rank": int(n_units),
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "multi_gpu": None if world == 1 else {"unit_list_owner": "rank 0", "scatter_ms": scatter_ms,
+                                                  "partition": "contiguous ranges balanced by compressed+decompressed bytes (shard.partition)",
+                                                  "legs": legs},
         }
         print(json.dumps(line))
     if world > 1:
@@ -368,6 +457,8 @@ def main():
     ap.add_argument("--e2e-units", type=int, default=N_UNITS)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-legs", action="store_true")
+    ap.add_argument("--leg-units", type=int, default=32768)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

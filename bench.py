@@ -225,6 +225,7 @@ def run_product(args):
     dev = torch.device(f"cuda:{local}")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_%h_%p.log")     # NCCL's version / debug lines go to a file: stdout = the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
     L.swc_timing_collect.argtypes = [C.c_void_p, C.c_int32]

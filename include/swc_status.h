@@ -84,7 +84,20 @@ enum swc_status {
     SWC_XZ_WRONG_DATA_SIZE          = 806,
     SWC_XZ_WRONG_CHECK              = 807,  /* payload-carrying */
     SWC_XZ_WRONG_PADDING            = 808,
-    SWC_XZ_MULTI_BYTE_INTEGER_ERROR = 809
+    SWC_XZ_MULTI_BYTE_INTEGER_ERROR = 809,
+
+    /* ZipError, Sources/ZIP/ZipError.swift:12-36 */
+    SWC_ZIP_NOT_FOUND_CENTRAL_DIRECTORY_END = 901,
+    SWC_ZIP_WRONG_SIGNATURE            = 902,
+    SWC_ZIP_WRONG_SIZE                 = 903,
+    SWC_ZIP_WRONG_VERSION              = 904,
+    SWC_ZIP_MULTI_VOLUMES_NOT_SUPPORTED = 905,
+    SWC_ZIP_ENCRYPTION_NOT_SUPPORTED   = 906,
+    SWC_ZIP_PATCHING_NOT_SUPPORTED     = 907,
+    SWC_ZIP_COMPRESSION_NOT_SUPPORTED  = 908,
+    SWC_ZIP_WRONG_LOCAL_HEADER         = 909,
+    SWC_ZIP_WRONG_CRC                  = 910,  /* payload-carrying: the entries processed so far, the failing one last */
+    SWC_ZIP_WRONG_TEXT_FIELD           = 911
 };
 
 #endif /* SWC_STATUS_H */

@@ -178,6 +178,29 @@ int32_t swc_xz_unarchive(const uint8_t *in, size_t in_len, uint8_t **out, size_t
 int32_t swc_xz_split_unarchive(const uint8_t *in, size_t in_len,
                                uint8_t **out, size_t *out_len, size_t **stream_ends, size_t *n_streams);
 
+/* ---- ZIP container -------------------------------------------------------------------------------------------
+ * ZipContainer.open(container:) -> [ZipEntry]     Sources/ZIP/ZipContainer.swift:43-58 (entry data: getEntryData :62-125)
+ * ZipContainer.info(container:) -> [ZipEntryInfo] Sources/ZIP/ZipContainer.swift:132-134 (host only, no device needed)
+ * One entry per central-directory record, in its order.  All Deflate / BZip2 / LZMA entries of a container are decoded as
+ * one batch each; errors (and the entries returned with SWC_ZIP_WRONG_CRC: the failing one last) are those of the reference's
+ * entry-by-entry loop.  `*out` holds every entry's data at [data_off, data_off + data_len); free both results with swc_free. */
+typedef struct swc_zip_entry {
+    uint64_t name_off, name_len;         /* ZipEntryInfo.name: bytes inside the container (central directory) */
+    uint64_t comment_off, comment_len;   /* ZipEntryInfo.comment */
+    uint64_t data_off, data_len;         /* ZipEntry.data inside *out (0, 0 for directories and for swc_zip_info) */
+    uint64_t size;                       /* ZipEntryInfo.size */
+    uint32_t crc;                        /* ZipEntryInfo.crc */
+    uint32_t external_attrs;             /* externalFileAttributes: permissions = (attrs & 0x0FFF0000) >> 16, dosAttributes = attrs & 0xFF */
+    uint16_t method;                     /* raw compression method: 0 copy, 8 deflate, 12 bzip2, 14 lzma, else .other */
+    uint16_t version_made_by;            /* FileSystemType(versionMadeBy) */
+    uint16_t internal_attrs;             /* isTextFile = internal_attrs & 1 */
+    uint16_t dos_time, dos_date;         /* native modification time */
+    uint8_t  is_directory;               /* ZipEntryInfo.type == .directory */
+    uint8_t  utf8;                       /* general purpose bit 11: name / comment are UTF-8 (else CP437 unless the bytes need UTF-8) */
+} swc_zip_entry;
+int32_t swc_zip_open(const uint8_t *in, size_t in_len, uint8_t **out, size_t *out_len, swc_zip_entry **entries, size_t *n_entries);
+int32_t swc_zip_info(const uint8_t *in, size_t in_len, swc_zip_entry **entries, size_t *n_entries);
+
 /* ---- checks (device-side, used by the wrappers; exposed for the shim and the tests) ---------------------------
  * CheckSums.crc32 / bzip2crc32 / crc64 / adler32   Sources/Common/CheckSums.swift:12-57
  * XxHash32.hash                                     Sources/LZ4/XxHash32.swift:24-83

@@ -195,3 +195,28 @@ def batch_mt(codec, units, total, threads, aux=0):
     if rc != 0:
         raise RuntimeError("swco_batch_mt could not start its threads")
     return sec.value, nbytes.value, fails.value
+
+
+class _ZipEntry(C.Structure):
+    _fields_ = [("name_off", C.c_uint64), ("name_len", C.c_uint64), ("comment_off", C.c_uint64), ("comment_len", C.c_uint64),
+                ("data_off", C.c_uint64), ("data_len", C.c_uint64), ("size", C.c_uint64), ("crc", C.c_uint32),
+                ("external_attrs", C.c_uint32), ("method", C.c_uint16), ("version_made_by", C.c_uint16),
+                ("internal_attrs", C.c_uint16), ("dos_time", C.c_uint16), ("dos_date", C.c_uint16), ("is_directory", C.c_uint8),
+                ("utf8", C.c_uint8)]
+
+
+def zip_open(data, info_only=False, max_entries=1 << 16):
+    """ZipContainer.open(container:) / info(container:) -> (status, [dict(name, comment, data, size, crc, method, is_directory, utf8)])"""
+    data = bytes(data)
+    buf, n = _Buf(), C.c_size_t(0)
+    ents = (_ZipEntry * max_entries)()
+    st = lib().swco_zip_open(_ptr(data), C.c_size_t(len(data)), C.byref(buf), ents, C.c_size_t(max_entries), C.byref(n), C.c_int(1 if info_only else 0))
+    whole = _take(buf)
+    out = []
+    for i in range(min(n.value, max_entries)):
+        e = ents[i]
+        out.append(dict(name=data[e.name_off:e.name_off + e.name_len], comment=data[e.comment_off:e.comment_off + e.comment_len],
+                        data=None if (e.is_directory or info_only) else whole[e.data_off:e.data_off + e.data_len],
+                        size=e.size, crc=e.crc, method=e.method, is_directory=bool(e.is_directory), utf8=bool(e.utf8),
+                        external_attrs=e.external_attrs, version_made_by=e.version_made_by, dos_time=e.dos_time, dos_date=e.dos_date))
+    return st, out

@@ -75,6 +75,8 @@ def lib():
         L.swc_zlib_header_parse.argtypes = [vp, sz, vp]
         L.swc_lzma_decompress_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, u64, vp]
         L.swc_crc32_batch.argtypes = [vp, vp, vp, vp, vp, u64, vp]
+        L.swc_zip_open.argtypes = [vp, sz, C.POINTER(vp), szp, C.POINTER(vp), szp]
+        L.swc_zip_info.argtypes = [vp, sz, C.POINTER(vp), szp]
         L.swc_xxh32_batch.argtypes = [vp, vp, vp, vp, u64, vp]
         L.swc_zlib_unarchive.argtypes = [vp, sz, C.POINTER(vp), szp]
         L.swc_xz_unarchive.argtypes = [vp, sz, C.POINTER(vp), szp]

@@ -20,7 +20,7 @@ from dataclasses import dataclass, field
 from . import _lib
 from .errors import check, error_for
 
-_PAYLOAD_CODES = {210, 503, 605, 705, 807}
+_PAYLOAD_CODES = {210, 503, 605, 705, 807, 910}
 
 
 def _single(fn, data, *extra, consumed=True):
@@ -242,6 +242,109 @@ class XZArchive:
     @staticmethod
     def splitUnarchive(archive):
         return _multi("swc_xz_split_unarchive", archive)
+
+
+class _CZipEntry(C.Structure):
+    _fields_ = [("name_off", C.c_uint64), ("name_len", C.c_uint64), ("comment_off", C.c_uint64), ("comment_len", C.c_uint64),
+                ("data_off", C.c_uint64), ("data_len", C.c_uint64), ("size", C.c_uint64), ("crc", C.c_uint32),
+                ("external_attrs", C.c_uint32), ("method", C.c_uint16), ("version_made_by", C.c_uint16),
+                ("internal_attrs", C.c_uint16), ("dos_time", C.c_uint16), ("dos_date", C.c_uint16), ("is_directory", C.c_uint8),
+                ("utf8", C.c_uint8)]
+
+
+_ZIP_METHODS = {0: "copy", 8: "deflate", 12: "bzip2", 14: "lzma"}
+
+
+def _zip_text(raw, utf8):
+    """zipString (LittleEndianByteReader+Zip.swift:11-24): UTF-8 when flagged, or when the bytes only make sense as UTF-8;
+    CP437 otherwise.  The library has already rejected what String(data:encoding:) would."""
+    if utf8:
+        return raw.decode("utf-8")
+    try:
+        if any(b >= 0x80 for b in raw):
+            return raw.decode("utf-8")
+    except UnicodeDecodeError:
+        pass
+    return raw.decode("cp437")
+
+
+@dataclass
+class ZipEntryInfo:
+    """Sources/ZIP/ZipEntryInfo.swift:9-95 (the fields the container walk itself produces)"""
+    name: str
+    size: int
+    type: str                       # "directory" | "regular" (other Unix types are reported as "regular" here)
+    compressionMethod: str
+    crc: int
+    comment: str
+    isTextFile: bool
+    externalFileAttributes: int
+    permissions: int
+    dosAttributes: int
+    versionMadeBy: int
+    modificationTime: datetime.datetime = None
+
+
+@dataclass
+class ZipEntry:
+    """Sources/ZIP/ZipEntry.swift:9-20"""
+    info: ZipEntryInfo
+    data: bytes = None
+
+
+def _zip_infos(container, es, count):
+    arr = C.cast(es, C.POINTER(_CZipEntry))
+    out = []
+    for i in range(count):
+        e = arr[i]
+        d, t = e.dos_date, e.dos_time
+        try:
+            mt = datetime.datetime(1980 + ((d & 0xFE00) >> 9), (d & 0x1E0) >> 5, d & 0x1F, (t & 0xF800) >> 11, (t & 0x7E0) >> 5, 2 * (t & 0x1F))
+        except ValueError:
+            mt = None
+        info = ZipEntryInfo(name=_zip_text(container[e.name_off:e.name_off + e.name_len], e.utf8), size=e.size,
+                            type="directory" if e.is_directory else "regular",
+                            compressionMethod=_ZIP_METHODS.get(e.method, "other"), crc=e.crc,
+                            comment=_zip_text(container[e.comment_off:e.comment_off + e.comment_len], e.utf8),
+                            isTextFile=bool(e.internal_attrs & 1), externalFileAttributes=e.external_attrs,
+                            permissions=(e.external_attrs & 0x0FFF0000) >> 16, dosAttributes=e.external_attrs & 0xFF,
+                            versionMadeBy=e.version_made_by, modificationTime=mt)
+        out.append((info, e.data_off, e.data_len, bool(e.is_directory)))
+    return out
+
+
+class ZipContainer:
+    """Sources/ZIP/ZipContainer.swift:10-180"""
+
+    @staticmethod
+    def info(container):
+        data = bytes(container)
+        buf, n = _lib.inbuf(data)
+        es, cnt = C.c_void_p(), C.c_size_t(0)
+        st = _lib.lib().swc_zip_info(buf, n, C.byref(es), C.byref(cnt))
+        try:
+            check(st)
+            return [x[0] for x in _zip_infos(data, es, cnt.value)]
+        finally:
+            if es.value:
+                _lib.lib().swc_free(es)
+
+    @staticmethod
+    def open(container):
+        """-> [ZipEntry]; ZipError.wrongCRC carries the entries processed so far, the failing one last (ZipContainer.swift:53-55)."""
+        data = bytes(container)
+        buf, n = _lib.inbuf(data)
+        out, out_len, es, cnt = C.c_void_p(), C.c_size_t(0), C.c_void_p(), C.c_size_t(0)
+        st = _lib.lib().swc_zip_open(buf, n, C.byref(out), C.byref(out_len), C.byref(es), C.byref(cnt))
+        try:
+            whole = _lib.take(out, out_len)
+            entries = [ZipEntry(info, None if is_dir else whole[off:off + ln]) for info, off, ln, is_dir in _zip_infos(data, es, cnt.value)]
+        finally:
+            if es.value:
+                _lib.lib().swc_free(es)
+        if st != 0:
+            raise error_for(st, entries if st in _PAYLOAD_CODES else None)
+        return entries
 
 
 # ---- checks (CheckSums.swift / XxHash32.swift / Sha256.swift) ----

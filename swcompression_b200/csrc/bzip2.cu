@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(WARPS * 32) bzip2_kernel(Args a) {
                 if (lane == 0) selectors[i] = (u8)el;
             }
         }
+        bool any_over = false;
         for (int t = 0; t < ntab; t++) {              // code lengths :177-203
             if (br.avail < 5) FAIL(SWC_BZIP2_WRONG_HUFFMAN_CODE_LENGTH);
             int length = (int)br.get(5);
@@ -278,9 +279,10 @@ __global__ void __launch_bounds__(WARPS * 32) bzip2_kernel(Args a) {
                 if (lane == 0) S.limit[t][L - 1] = code > (1u << 20) ? (1u << 20) : code;
             }
             if (lane == 0) for (int L = MAX_LEN; L < 32; L++) S.limit[t][L] = 1u << 20;
-            if (over) FAIL(SWC_ERR_UNSUPPORTED);      // over-subscribed set (heap-overwrite semantics): not taken by this kernel
+            any_over = any_over || over;              // reported after ALL tables are read: a bad length further on comes first in the reference
             __syncwarp();
         }
+        if (any_over) FAIL(SWC_ERR_UNSUPPORTED);      // over-subscribed set (heap-overwrite semantics): not taken by this kernel
         __syncwarp();
         if (nsel == 0) FAIL(SWC_ERR_REFERENCE_TRAP);                                 // selectors[0]
 

@@ -265,6 +265,17 @@ const char *swc_status_name(int32_t s) {
     case SWC_XZ_WRONG_CHECK: return "XZError.wrongCheck";
     case SWC_XZ_WRONG_PADDING: return "XZError.wrongPadding";
     case SWC_XZ_MULTI_BYTE_INTEGER_ERROR: return "XZError.multiByteIntegerError";
+    case SWC_ZIP_NOT_FOUND_CENTRAL_DIRECTORY_END: return "ZipError.notFoundCentralDirectoryEnd";
+    case SWC_ZIP_WRONG_SIGNATURE: return "ZipError.wrongSignature";
+    case SWC_ZIP_WRONG_SIZE: return "ZipError.wrongSize";
+    case SWC_ZIP_WRONG_VERSION: return "ZipError.wrongVersion";
+    case SWC_ZIP_MULTI_VOLUMES_NOT_SUPPORTED: return "ZipError.multiVolumesNotSupported";
+    case SWC_ZIP_ENCRYPTION_NOT_SUPPORTED: return "ZipError.encryptionNotSupported";
+    case SWC_ZIP_PATCHING_NOT_SUPPORTED: return "ZipError.patchingNotSupported";
+    case SWC_ZIP_COMPRESSION_NOT_SUPPORTED: return "ZipError.compressionNotSupported";
+    case SWC_ZIP_WRONG_LOCAL_HEADER: return "ZipError.wrongLocalHeader";
+    case SWC_ZIP_WRONG_CRC: return "ZipError.wrongCRC";
+    case SWC_ZIP_WRONG_TEXT_FIELD: return "ZipError.wrongTextField";
     default: return "unknown";
     }
 }

@@ -3,7 +3,7 @@
 DeflateError (Sources/Deflate/DeflateError.swift:10-19), BZip2Error (Sources/BZip2/BZip2Error.swift:12-44),
 LZMAError (Sources/LZMA/LZMAError.swift:10-25), LZMA2Error (Sources/LZMA2/LZMA2Error.swift:10-22),
 DataError (Sources/Common/DataError.swift:9-25), GzipError (Sources/GZip/GzipError.swift:10-35),
-ZlibError (Sources/Zlib/ZlibError.swift:12-26), XZError (Sources/XZ/XZError.swift:12-48).
+ZlibError (Sources/Zlib/ZlibError.swift:12-26), XZError (Sources/XZ/XZError.swift:12-48), ZipError (Sources/ZIP/ZipError.swift:12-36).
 Payload-carrying cases (`wrongCRC(Data)`, `checksumMismatch([Data])`, ...) expose the decoded bytes as `.payload`.
 """
 
@@ -66,8 +66,15 @@ class XZError(SWCompressionError):
              806: "wrongDataSize", 807: "wrongCheck", 808: "wrongPadding", 809: "multiByteIntegerError"}
 
 
+class ZipError(SWCompressionError):
+    """Sources/ZIP/ZipError.swift:12-36; wrongCRC carries the entries processed so far (the failing one last)"""
+    cases = {901: "notFoundCentralDirectoryEnd", 902: "wrongSignature", 903: "wrongSize", 904: "wrongVersion",
+             905: "multiVolumesNotSupported", 906: "encryptionNotSupported", 907: "patchingNotSupported",
+             908: "compressionNotSupported", 909: "wrongLocalHeader", 910: "wrongCRC", 911: "wrongTextField"}
+
+
 _BY_RANGE = [(1, 99, EngineError), (101, 199, DeflateError), (201, 299, BZip2Error), (301, 399, LZMAError),
-             (401, 499, LZMA2Error), (501, 599, DataError), (601, 699, GzipError), (701, 799, ZlibError), (801, 899, XZError)]
+             (401, 499, LZMA2Error), (501, 599, DataError), (601, 699, GzipError), (701, 799, ZlibError), (801, 899, XZError), (901, 999, ZipError)]
 
 
 def error_for(code, payload=None):

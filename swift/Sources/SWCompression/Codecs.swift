@@ -203,3 +203,36 @@ public class XZArchive: Archive {                                    // Sources/
         try multi(data) { p, n, o, ol, e, c in swc_xz_split_unarchive(p, n, o, ol, e, c) }
     }
 }
+
+// ---- ZIP container (Sources/ZIP/ZipContainer.swift:10-180) -------------------------------------------------------------
+/// `ZipContainer.open(container:)`: the engine walks the central directory once, decodes every entry of a method as one batch
+/// and returns the entries in central-directory order.  ZipEntryInfo's remaining metadata (timestamps from extra fields,
+/// owner ids, custom extra fields) stays in Swift: ZipEntryInfo.swift / BuiltinExtraFields.swift are unchanged and read the
+/// same bytes; the engine supplies name, comment, size, crc, method, attributes and the entry data.
+public class ZipContainer: Container {
+    public static func open(container data: Data) throws -> [ZipEntry] {
+        var out: UnsafeMutablePointer<UInt8>? = nil, outLen = 0
+        var es: UnsafeMutablePointer<swc_zip_entry>? = nil, count = 0
+        let st = data.withUnsafeBytes { raw in
+            swc_zip_open(raw.bindMemory(to: UInt8.self).baseAddress, raw.count, &out, &outLen, &es, &count)
+        }
+        defer { swc_free(out); swc_free(es) }
+        var entries = [ZipEntry]()
+        for i in 0..<count {
+            let e = es![i]
+            let info = ZipEntryInfo(container: data, engineEntry: e)                 // thin init added next to the reference's
+            let payload = e.is_directory != 0 ? nil : Data(bytes: out! + Int(e.data_off), count: Int(e.data_len))
+            entries.append(ZipEntry(info, payload))
+        }
+        if st == 910 { throw ZipError.wrongCRC(entries) }                            // SWC_ZIP_WRONG_CRC; ZipContainer.swift:53-55
+        guard st == 0 else { throw swcError(st) }
+        return entries
+    }
+    public static func info(container data: Data) throws -> [ZipEntryInfo] {
+        var es: UnsafeMutablePointer<swc_zip_entry>? = nil, count = 0
+        let st = data.withUnsafeBytes { raw in swc_zip_info(raw.bindMemory(to: UInt8.self).baseAddress, raw.count, &es, &count) }
+        defer { swc_free(es) }
+        guard st == 0 else { throw swcError(st) }
+        return (0..<count).map { ZipEntryInfo(container: data, engineEntry: es![$0]) }
+    }
+}

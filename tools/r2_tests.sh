@@ -1,2 +1,2 @@
 cd /root/repo
-python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+python -m pytest ${TESTS:-tests} -m gpu -x -q 2>&1 | tail -15

@@ -7,7 +7,7 @@
 // 32 different streams per warp, persistent lanes fed by a ticket counter.  A warp works in rounds that start with a
 // full-mask vote (lanes stay in lock step):
 //   top-up : every lane keeps an 8-word ring of its compressed stream in shared memory; a lane whose ring is half empty
-//            stores the 16-byte chunk it prefetched a round earlier (ld.global.nc.L1::no_allocate.v4) and issues the next
+//            stores the 16-byte chunk it prefetched a round earlier (one LDG.128 per lane) and issues the next
 //            load — the only place global input is touched, so the load latency never sits on the decode chain.
 //   fast   : up to KLIT table lookups per lane: peek (funnel shift of a 64-bit register window) -> 2^8-entry 16-bit LUT in
 //            shared memory, halfword-interleaved across the warp (entry h of lane l at halfword h*32+l: at most a 2-way bank
@@ -110,7 +110,9 @@ __device__ __forceinline__ uint4 load_chunk(const Span &sp, u32 ch) {
     const u8 *c = sp.origin + (size_t)ch * 16;
     if (c >= sp.ubeg && c + 16 <= sp.uend) {
         uint4 v;
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(c));
+        // plain read-only 16-byte load.  (ld.global.nc.L1::no_allocate was measured at 203 KB of DRAM reads per 64 KiB unit instead
+        // of 74 KB: the hint also makes the line evict-first in L2, so the second 16-byte half of every sector came from DRAM again.)
+        v = __ldg((const uint4 *)c);
         return v;
     }
     return load_edge(c, sp.ubeg, sp.uend);

@@ -18,15 +18,6 @@ typedef int64_t i64;
 
 namespace swc {
 
-__device__ __forceinline__ uint4 ldg16(const uint4 *p) { return __ldg(p); }
-
-// streaming 16-byte load that does not pollute L1 (compressed input is read exactly once)
-__device__ __forceinline__ uint4 ld_stream16(const uint4 *p) {
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
-}
-
 __device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31; }
 
 // launch bookkeeping (swc_kernel_launches)

@@ -333,9 +333,12 @@ int launch(const Args &a, cudaStream_t stream) {
         u64 *base = (u64 *)a.scratch;
         u32 *cnt = (u32 *)(base + a.n);
         u64 *recs = (u64 *)(((uintptr_t)(cnt + a.n) + 255) & ~(uintptr_t)255);
+        timing_mark(stream);
         lz4_rec_scan_kernel<<<1, 1024, 0, stream>>>(a.blk_len, a.n, base);
         lz4_parse_kernel<<<(unsigned)((a.n + 127) / 128), 128, 0, stream>>>(a, base, recs, cnt);
+        timing_mark(stream);
         lz4_exec_kernel<<<(unsigned)((a.n * 32 + 255) / 256), 256, 0, stream>>>(a, base, recs, cnt);
+        timing_mark(stream);
         lz4_fallback_kernel<<<(unsigned)((a.n * 32 + 255) / 256), 256, 0, stream>>>(a);
         count_launch(4);
         SWC_CUDA_TRY(cudaGetLastError());

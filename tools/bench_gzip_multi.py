@@ -41,8 +41,8 @@ def main():
     t = time.perf_counter()
     parts = GzipArchive.multiUnarchive(data)
     dt = time.perf_counter() - t
-    assert len(parts) == n and all(parts[i] == raws[i % distinct] for i in range(0, n, 101))
-    out_bytes = sum(len(p) for p in parts)
+    assert len(parts) == n and all(parts[i].data == raws[i % distinct] for i in range(0, n, 101))
+    out_bytes = sum(len(p.data) for p in parts)
     sample = b"".join(blobs[:64])
     t = time.perf_counter()
     ost, _, whole = swco.gzip_multi_unarchive(sample)

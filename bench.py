@@ -61,6 +61,30 @@ def workload_config(n_units, distinct, world):
             "corpus": "order-1 Markov/Zipf text + back-references (tests/helpers.textlike), zlib level 6 raw deflate memLevel 9"}
 
 
+def host_memory_budget():
+    """Bytes of host memory this job may use: MemAvailable, clipped by the cgroup limit when there is one."""
+    avail = 1 << 62
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                avail = int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    for path in ("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory/memory.limit_in_bytes"):
+        try:
+            v = open(path).read().strip()
+            if v != "max":
+                lim = int(v)
+                try:
+                    used = int(open(path.replace("memory.max", "memory.current").replace("limit_in_bytes", "usage_in_bytes")).read())
+                except (OSError, ValueError):
+                    used = 0
+                avail = min(avail, max(lim - used, 0))
+        except (OSError, ValueError):
+            pass
+    return avail
+
+
 def read_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -382,6 +406,12 @@ def run_product(args):
     e2e = None
     if not args.no_e2e:
         n_e = min(args.e2e_units, n_units)
+        # every rank pins its own buffers: keep the job's pinned total under half of what the host (or its cgroup) can give
+        n_e = max(2048, min(n_e, int(host_memory_budget() * 0.5 / world / (UNIT * 1.4))))
+        if world > 1:                                                  # one figure for the whole job
+            tn = torch.tensor([n_e], dtype=torch.int64, device=dev)
+            dist.all_reduce(tn, op=dist.ReduceOp.MIN)
+            n_e = int(tn.item())
         in_total = int(all_off[n_e - 1] + l_stride[n_e - 1]) + 64
         out_total = n_e * UNIT
         p_in = L.swc_alloc_pinned(in_total)

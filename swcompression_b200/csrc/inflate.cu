@@ -547,8 +547,25 @@ lz_resolve_kernel(BatchArgs a) {
                 const bool ready = pend && (sub == oldest || src_end <= frontier);
                 if (ready) {
                     const u8 *src = out + s - d;
-                    if (d >= l) { for (u32 i = t; i < l; i += 4) out[s + i] = src[i]; }
-                    else        { for (u32 i = t; i < l; i += 4) out[s + i] = src[i % d]; }
+                    u8 *dst = out + s;
+                    if (d >= l) {
+                        // four bytes per lane and trip, all four loads issued before the first store (a match is 15 bytes on
+                        // average: one trip covers 16)
+                        for (u32 k = t; k < l; k += 16) {
+                            const bool p1 = k + 4 < l, p2 = k + 8 < l, p3 = k + 12 < l;
+                            const u8 b0 = src[k];
+                            u8 b1 = 0, b2 = 0, b3 = 0;
+                            if (p1) b1 = src[k + 4];
+                            if (p2) b2 = src[k + 8];
+                            if (p3) b3 = src[k + 12];
+                            dst[k] = b0;
+                            if (p1) dst[k + 4] = b1;
+                            if (p2) dst[k + 8] = b2;
+                            if (p3) dst[k + 12] = b3;
+                        }
+                    } else {
+                        for (u32 i = t; i < l; i += 4) dst[i] = src[i % d];
+                    }
                     pend = false;
                 }
                 __syncwarp();

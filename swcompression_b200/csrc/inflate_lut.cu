@@ -32,25 +32,32 @@ namespace k1l {
 #ifndef SWC_LB
 #define SWC_LB 7
 #endif
+#ifndef SWC_DB
+#define SWC_DB 5
+#endif
 constexpr int LB = SWC_LB;                  // lit/len LUT index bits
-constexpr int DB = 5;                       // distance LUT index bits
-// ---- per-lane shared memory: halfword area (entry h of lane l at H[h*32+l]) then word area (word w at W[w*32+l]) ----
+constexpr int DB = SWC_DB;                  // distance LUT index bits
+// ---- per-lane shared memory: halfword area (entry h of lane l at H[h*32+l]), byte area (D[h*32+l]), word area (W[w*32+l]) ----
 constexpr int H_LIT = 0;
-constexpr int H_DST = 1 << LB;
-constexpr int H_TOTAL = (1 << LB) + (1 << DB);          // 288 halfwords
-constexpr int W_LIT_BO = 0;                 // [1..15] first left-justified 15-bit code | index of its first LONG symbol << 16
-constexpr int W_DST_BO = 16;
-constexpr int W_CL_BO = 32;                 // [1..7]
-constexpr int W_CL_SYM = 40;                // 19 x u8
-constexpr int W_TOTAL = 45;
+constexpr int H_TOTAL = 1 << LB;            // lit/len LUT, 16-bit entries
+constexpr int D_TOTAL = 1 << DB;            // distance LUT, 8-bit entries {code length:3 | symbol:5}, 0 = no code of <= DB bits
+// word area in the symbol phase: for every code length the LUT does not cover, {first left-justified 15-bit code | index of its
+// first symbol in the long-symbol list << 16}
+constexpr int W_LONG_LIT = 0;               // lengths LB+1 .. 15
+constexpr int W_LONG_DST = 15 - LB;         // lengths DB+1 .. 15
+constexpr int W_TOTAL = (15 - LB) + (15 - DB);
+// the same words while a header is parsed (the code-length alphabet is dead once the LUTs are filled)
+constexpr int W_CL_BO = 0;                  // [1..7]
+constexpr int W_CL_SYM = 8;                 // 19 x u8
+static_assert(W_CL_SYM + 5 <= W_TOTAL, "code-length tables must fit the long-code words they alias");
 constexpr int RING_BYTES = 8 * 32 * 4;      // per warp: 8 words of compressed input per lane; 1 KiB, 1 KiB-aligned (address wrap by mask)
-constexpr int WARP_BYTES = H_TOTAL * 32 * 2 + W_TOTAL * 32 * 4;
+constexpr int WARP_BYTES = H_TOTAL * 32 * 2 + D_TOTAL * 32 + W_TOTAL * 32 * 4;
 #ifndef SWC_K1L_WARPS
-#define SWC_K1L_WARPS 3
+#define SWC_K1L_WARPS 4
 #define SWC_K1L_CTAS 4
 #endif
 constexpr int WARPS_PER_CTA = SWC_K1L_WARPS;
-constexpr int CTAS_PER_SM = SWC_K1L_CTAS;   // 12 warps per SM with a 2^7-entry LUT (17 KB per warp)
+constexpr int CTAS_PER_SM = SWC_K1L_CTAS;   // 16 warps per SM with a 2^7-entry LUT (12.3 KB per warp)
 constexpr int LUT_WORDS = 64;               // CTA-shared length / distance base+extra tables
 // CTA layout: [rings: WARPS x 1 KiB][LUT_WORDS x 4][per-warp tables]
 constexpr size_t SMEM_BYTES = (size_t)WARPS_PER_CTA * RING_BYTES + LUT_WORDS * 4 + (size_t)WARPS_PER_CTA * WARP_BYTES;
@@ -58,7 +65,8 @@ constexpr size_t SMEM_BYTES = (size_t)WARPS_PER_CTA * RING_BYTES + LUT_WORDS * 4
 #ifndef SWC_KLIT2
 #define SWC_KLIT2 8
 #endif
-constexpr int KLIT = SWC_KLIT2;             // lookups a lane may do per round (<= 48 bits) before parked symbols are serviced
+constexpr int KLIT = SWC_KLIT2;             // lookups a lane may do per round (<= 56 bits) before parked symbols are serviced
+static_assert(SWC_KLIT2 <= 8, "at most one 8-byte literal word may fill up per round (deferred store)");
 
 constexpr u32 E_NONLIT = 0x8000u;           // LUT entry: bit15 = not a literal; [11:8] code length (0 = long / no code)
 constexpr u32 CODE_EOB = 31;                //   non-literal low byte: 0..28 length symbol 257+k, 29/30 = 286/287, 31 = end of block
@@ -126,10 +134,16 @@ __device__ __forceinline__ u32 lut_addr(u32 index, u32 base) { u32 a; asm("mad.l
 // ------------------------------------------------------------------------------------------------ symbol-phase bit reader
 // Window (lo, hi) = stream words [wend/32 - 1, wend/32]; further words wait in the shared-memory ring (slot = word index & 7,
 // slot k of lane l at ring + k*128 + l*4; the ring of a warp is 1 KiB-aligned so the slot address wraps with one LOP3).
+#ifndef SWC_NXT
+#define SWC_NXT 1
+#endif
 struct Reader {
     u32 lo, hi;
+#if SWC_NXT
+    u32 nxt;          // stream word wend/32 + 1, popped one step early so that no shared-memory load sits on the decode chain
+#endif
     u32 pos;          // absolute bit position of the next unread bit;  wend - 32 <= pos < wend + 32
-    u32 wend;         // bit position where `hi` starts; the next word to pop has index wend/32 + 1
+    u32 wend;         // bit position where `hi` starts; the next word to pop has index wend/32 + 1 (+ 2 with `nxt`)
     u32 rptr;         // shared-memory address of that word's slot
     u32 wr;           // next word index to push into the ring
     u32 nextc;        // chunk index after `pre`
@@ -138,13 +152,33 @@ struct Reader {
     __device__ __forceinline__ u32 peek32() const { return __funnelshift_r(lo, hi, pos); }   // requires pos < wend
     __device__ __forceinline__ void advance() {                                                // requires pos >= wend
         lo = hi;
+#if SWC_NXT
+        hi = nxt;
+        nxt = lds32(rptr);
+#else
         hi = lds32(rptr);
+#endif
         const u32 t = rptr + 128;
         rptr = (t & 0x380u) | (rptr & ~0x380u);
         wend += 32;
     }
+    // `if (pos >= wend) advance()` without a branch: the slot is read either way
+    __device__ __forceinline__ void refill() {
+        const bool adv = pos >= wend;
+        const u32 nw = lds32(rptr);
+        const u32 t = rptr + 128;
+        lo = adv ? hi : lo;
+#if SWC_NXT
+        hi = adv ? nxt : hi;
+        nxt = adv ? nw : nxt;
+#else
+        hi = adv ? nw : hi;
+#endif
+        rptr = adv ? ((t & 0x380u) | (rptr & ~0x380u)) : rptr;
+        wend = adv ? wend + 32 : wend;
+    }
     __device__ __forceinline__ void topup(u32 *ring, const Span &sp) {
-        if (wr - (wend >> 5) <= 5) {                               // <= 4 unread words in the ring: chunk wr/4 - 2 is consumed
+        if (wr - (wend >> 5) <= 5 + SWC_NXT) {                     // <= 4 unread words in the ring: chunk wr/4 - 2 is consumed
             u32 *s = ring + (wr & 4) * 32;
             s[0] = pre.x; s[32] = pre.y; s[64] = pre.z; s[96] = pre.w;
             wr += 4;
@@ -163,7 +197,10 @@ struct Reader {
         wr = (ch + 2) * 4;
         lo = ring[(w0 & 7) * 32];
         hi = ring[((w0 + 1) & 7) * 32];
-        rptr = (u32)__cvta_generic_to_shared(ring + ((w0 + 2) & 7) * 32);
+#if SWC_NXT
+        nxt = ring[((w0 + 2) & 7) * 32];
+#endif
+        rptr = (u32)__cvta_generic_to_shared(ring + ((w0 + 2 + SWC_NXT) & 7) * 32);
         wend = (w0 + 1) * 32;
         pos = bit;
     }
@@ -210,6 +247,22 @@ struct Emit {
             dirty = false;
         }
     }
+    // fast-loop form: the word that fills up (at most one per round, KLIT <= 8) is parked in (f_lo, f_hi) and stored after the
+    // loop at a convergent point, at [(op & ~7) - 8, op & ~7)
+    __device__ __forceinline__ void literal_deferred(u32 e, u32 &f_lo, u32 &f_hi, bool &full) {
+        acc_lo = __funnelshift_r(acc_lo, acc_hi, 8);
+        acc_hi = __funnelshift_r(acc_hi, e, 8);
+        op++;
+        const bool fill = (op & 7) == 0;
+        f_lo = fill ? acc_lo : f_lo;
+        f_hi = fill ? acc_hi : f_hi;
+        full = full || fill;
+        dirty = !fill;
+    }
+    __device__ __forceinline__ void store_deferred(u32 f_lo, u32 f_hi) {
+        const u32 p = op & ~7u;                                // the filled word ends here
+        if (p <= cap) *(uint2 *)(out + p - 8) = make_uint2(f_lo, f_hi);
+    }
     // the k = op & 7 bytes of the unfinished word, moved down to byte 0 (bytes above k are zero)
     __device__ __forceinline__ uint2 partial_word() const {
         const u32 sh = 8 * (8 - (op & 7));                     // 8..56
@@ -253,13 +306,14 @@ struct Emit {
 // ------------------------------------------------------------------------------------------------ table construction
 // finalize one alphabet: bo[L] holds count[L] on entry, {first_code_lj | first_long_index << 16} on exit; `lutbits` = codes of
 // at most that many bits live in the LUT and are not indexed.  Returns the Kraft sum scaled to 2^15.
+template <int STRIDE>
 __device__ __forceinline__ u32 finalize_tables(u32 *bo, Limits &lim, int maxlen, int lutbits) {
     u32 code = 0, off = 0;
     u32 l[17];
 #pragma unroll
     for (int L = 1; L <= 15; L++) {
-        u32 c = L <= maxlen ? bo[L * 32] : 0;
-        if (L <= maxlen) bo[L * 32] = (code & 0xFFFF) | (off << 16);
+        u32 c = L <= maxlen ? bo[L * STRIDE] : 0;
+        if (L <= maxlen) bo[L * STRIDE] = (code & 0xFFFF) | (off << 16);
         code += c << (15 - L);
         if (L > lutbits) off += c;
         l[L] = code > 0x8000u ? 0x8000u : code;
@@ -271,13 +325,14 @@ __device__ __forceinline__ u32 finalize_tables(u32 *bo, Limits &lim, int maxlen,
 }
 // after the assignment pass bo[L] = {end code of length L | end index}: the canonical property makes that the first
 // code / index of length L+1, so shifting the array up by one slot restores the "first" values
+template <int STRIDE>
 __device__ __forceinline__ void rewind_tables(u32 *bo, int maxlen) {
     u32 prev = 0;
 #pragma unroll
     for (int L = 1; L <= 15; L++) {
         if (L <= maxlen) {
-            const u32 w = bo[L * 32];
-            bo[L * 32] = prev;
+            const u32 w = bo[L * STRIDE];
+            bo[L * STRIDE] = prev;
             prev = w;
         }
     }
@@ -289,9 +344,11 @@ __device__ __forceinline__ int static_len(int i) {   // i < 288: lit/len, else d
 
 struct LaneMem {
     u16 *H;        // this lane's halfword 0
+    u8 *D;         // this lane's byte 0 of the distance LUT
     u32 *W;        // this lane's word 0
     u16 *longsym;  // lit/len symbols with codes longer than LB bits, in canonical order (local memory)
     u8 *longdst;   // distance symbols with codes longer than DB bits (local memory)
+    u32 *bol, *bod; // header phase: per-length counters, then code / long-index cursors, [1..15] (local memory)
 };
 
 // code-length alphabet: canonical decode (<= 7-bit codes, 19 symbols)
@@ -343,7 +400,7 @@ __device__ int run_lengths(HeaderBits &hb, const LaneMem &M, const Limits &cl_li
         } else {
             for (int r = 0; r < reps; r++, n++) {
                 const bool is_lit = n < hlit;
-                u32 *bo = M.W + ((is_lit ? W_LIT_BO : W_DST_BO) + len) * 32;
+                u32 *bo = (is_lit ? M.bol : M.bod) + len;
                 if (PASS == 0) {
                     *bo += 1;
                 } else {
@@ -352,13 +409,15 @@ __device__ int run_lengths(HeaderBits &hb, const LaneMem &M, const Limits &cl_li
                     const u32 sym = is_lit ? (u32)n : (u32)(n - hlit);
                     if (len <= lutbits) {
                         *bo = w + (1u << (15 - len));
-                        u32 e;
-                        if (!is_lit) e = ((u32)len << 8) | sym;
-                        else if (sym < 256) e = ((u32)len << 8) | sym;
-                        else e = E_NONLIT | ((u32)len << 8) | (sym == 256 ? CODE_EOB : sym - 257);
-                        u16 *lut = M.H + (is_lit ? H_LIT : H_DST) * 32;
                         const u32 step = 1u << len, lim = 1u << lutbits;
-                        for (u32 k = __brev(w & 0xFFFFu) >> 17; k < lim; k += step) lut[k * 32] = (u16)e;
+                        if (!is_lit) {
+                            for (u32 k = __brev(w & 0xFFFFu) >> 17; k < lim; k += step) M.D[k * 32] = (u8)(((u32)len << 5) | sym);
+                        } else {
+                            u32 e;
+                            if (sym < 256) e = ((u32)len << 8) | sym;
+                            else e = E_NONLIT | ((u32)len << 8) | (sym == 256 ? CODE_EOB : sym - 257);
+                            for (u32 k = __brev(w & 0xFFFFu) >> 17; k < lim; k += step) M.H[(H_LIT + k) * 32] = (u16)e;
+                        }
                     } else {
                         *bo = w + (1u << (15 - len)) + 0x10000u;
                         const u32 pos = w >> 16;
@@ -407,7 +466,7 @@ __device__ __forceinline__ int begin_block(HeaderBits &hb, Emit &em, const LaneM
     Limits cl_lim;
     u32 lens_pos = hb.pos;
 #pragma unroll
-    for (int L = 1; L <= 15; L++) { M.W[(W_LIT_BO + L) * 32] = 0; M.W[(W_DST_BO + L) * 32] = 0; }
+    for (int L = 1; L <= 15; L++) { M.bol[L] = 0; M.bod[L] = 0; }
     if (dynamic) {
         if (hb.avail() < 14) return SWC_DEFLATE_SYMBOL_NOT_FOUND;
         hlit = (int)hb.take(5) + 257;
@@ -421,7 +480,7 @@ __device__ __forceinline__ int begin_block(HeaderBits &hb, Emit &em, const LaneM
         for (int s = 0; s < 19; s++) cnt += 1ull << (8 * ((cl >> (3 * s)) & 7));
 #pragma unroll
         for (int L = 1; L <= 7; L++) M.W[(W_CL_BO + L) * 32] = (u32)(cnt >> (8 * L)) & 0xFF;
-        const u32 kraft = finalize_tables(M.W + W_CL_BO * 32, cl_lim, 7, 0);
+        const u32 kraft = finalize_tables<32>(M.W + W_CL_BO * 32, cl_lim, 7, 0);
         if (kraft > 0x8000u) return SWC_INTERNAL_NEEDS_SLOW;
         for (int s = 0; s < 19; s++) {
             const u32 l = (u32)(cl >> (3 * s)) & 7;
@@ -432,20 +491,25 @@ __device__ __forceinline__ int begin_block(HeaderBits &hb, Emit &em, const LaneM
                 ((u8 *)(M.W + (W_CL_SYM + (pos >> 2)) * 32))[pos & 3] = (u8)s;
             }
         }
-        rewind_tables(M.W + W_CL_BO * 32, 7);
+        rewind_tables<32>(M.W + W_CL_BO * 32, 7);
         lens_pos = hb.pos;
     }
     int st = run_lengths<0>(hb, M, cl_lim, dynamic, hlit, hdist);
     if (st) return st;
-    const u32 k1 = finalize_tables(M.W + W_LIT_BO * 32, bc.lit_lim, 15, LB);
-    const u32 k2 = finalize_tables(M.W + W_DST_BO * 32, bc.dst_lim, 15, DB);
+    const u32 k1 = finalize_tables<1>(M.bol, bc.lit_lim, 15, LB);
+    const u32 k2 = finalize_tables<1>(M.bod, bc.dst_lim, 15, DB);
     if (k1 > 0x8000u || k2 > 0x8000u) return SWC_INTERNAL_NEEDS_SLOW;
     for (int k = 0; k < (1 << LB); k++) M.H[(H_LIT + k) * 32] = (u16)E_NONLIT;     // "no short code here": canonical decoder decides
-    for (int k = 0; k < (1 << DB); k++) M.H[(H_DST + k) * 32] = 0;
+    for (int k = 0; k < (1 << DB); k++) M.D[k * 32] = 0;
     hb.pos = lens_pos;
     run_lengths<1>(hb, M, cl_lim, dynamic, hlit, hdist);
-    rewind_tables(M.W + W_LIT_BO * 32, 15);
-    rewind_tables(M.W + W_DST_BO * 32, 15);
+    rewind_tables<1>(M.bol, 15);
+    rewind_tables<1>(M.bod, 15);
+    // the symbol phase only needs the lengths the LUTs do not cover: they replace the code-length tables in shared memory
+#pragma unroll
+    for (int L = LB + 1; L <= 15; L++) M.W[(W_LONG_LIT + L - LB - 1) * 32] = M.bol[L];
+#pragma unroll
+    for (int L = DB + 1; L <= 15; L++) M.W[(W_LONG_DST + L - DB - 1) * 32] = M.bod[L];
     next = ST_SYMBOLS;
     return SWC_OK;
 }
@@ -460,7 +524,7 @@ __device__ __forceinline__ int parked_step(Reader &br, Emit &em, const LaneMem &
         const u32 r15 = __brev(w0 & 0x7FFFu) >> 17;
         const int CL = code_length(r15, bc.lit_lim);
         if (CL > 15) return SWC_DEFLATE_SYMBOL_NOT_FOUND;
-        const u32 w = M.W[(W_LIT_BO + CL) * 32];
+        const u32 w = M.W[(W_LONG_LIT + CL - LB - 1) * 32];          // CL > LB: the LUT holds every shorter code
         const u32 sym = M.longsym[(w >> 16) + ((r15 - (w & 0xFFFFu)) >> (15 - CL))];
         br.pos += CL;
         L = (u32)CL;
@@ -483,13 +547,13 @@ __device__ __forceinline__ int parked_step(Reader &br, Emit &em, const LaneMem &
     br.pos += eb;
     if (br.pos >= br.wend) br.advance();
     const u32 w32 = br.peek32();                                               // distance code (<= 15) + extra bits (<= 13)
-    const u32 de = M.H[(H_DST + (w32 & ((1u << DB) - 1))) * 32];
-    u32 DL = de >> 8, dsym = de & 0xFF;
+    const u32 de = M.D[(w32 & ((1u << DB) - 1)) * 32];
+    u32 DL = de >> 5, dsym = de & 31;
     if (DL == 0) {
         const u32 r15 = __brev(w32 & 0x7FFFu) >> 17;
         DL = (u32)code_length(r15, bc.dst_lim);
         if (DL > 15) return SWC_DEFLATE_SYMBOL_NOT_FOUND;
-        const u32 w = M.W[(W_DST_BO + DL) * 32];
+        const u32 w = M.W[(W_LONG_DST + DL - DB - 1) * 32];
         dsym = M.longdst[(w >> 16) + ((r15 - (w & 0xFFFFu)) >> (15 - DL))];
     }
     br.pos += DL;
@@ -517,9 +581,13 @@ inflate_lut_kernel(BatchArgs a) {
     u8 *wbase = (u8 *)(lut + LUT_WORDS) + (size_t)warp * WARP_BYTES;
     u16 longsym[288];
     u8 longdst[32];
+    u32 bol[16], bod[16];
     LaneMem M;
+    M.bol = bol;
+    M.bod = bod;
     M.H = (u16 *)wbase + lane;
-    M.W = (u32 *)(wbase + H_TOTAL * 32 * 2) + lane;
+    M.D = wbase + H_TOTAL * 32 * 2 + lane;
+    M.W = (u32 *)(wbase + H_TOTAL * 32 * 2 + D_TOTAL * 32) + lane;
     M.longsym = longsym;
     M.longdst = longdst;
     u32 *ring = smem + warp * (RING_BYTES / 4) + lane;
@@ -535,7 +603,11 @@ inflate_lut_kernel(BatchArgs a) {
     u64 cap64 = 0;
     u32 pend = 0;
     sp.origin = sp.ubeg = sp.uend = nullptr; sp.pos0 = sp.end = 0;
-    br.lo = br.hi = 0; br.pos = 0; br.wend = 32; br.rptr = 0; br.wr = 0; br.nextc = 0; br.pre = make_uint4(0, 0, 0, 0);
+    br.lo = br.hi = 0;
+#if SWC_NXT
+    br.nxt = 0;
+#endif
+    br.pos = 0; br.wend = 32; br.rptr = 0; br.wr = 0; br.nextc = 0; br.pre = make_uint4(0, 0, 0, 0);
     em.out = nullptr; em.rec = nullptr; em.op = 0; em.cap = 0; em.last_end = 0; em.nrec = 0; em.acc_lo = em.acc_hi = 0; em.dirty = false;
     for (;;) {
         if (state == ST_DONE) {
@@ -580,19 +652,22 @@ inflate_lut_kernel(BatchArgs a) {
             if (br.pos > sp.end) { status = SWC_DEFLATE_SYMBOL_NOT_FOUND; state = ST_DONE; }
         }
         // ---- fast: table lookups; a lane leaves the loop at its first non-literal ----
+        u32 f_lo = 0, f_hi = 0;
+        bool full = false;
         if (state == ST_SYMBOLS) {
 #pragma unroll
             for (int k = 0; k < KLIT; k++) {
-                if (br.pos >= br.wend) br.advance();
+                br.refill();
                 const u32 e = lds16(lut_addr(br.peek32() & ((1u << LB) - 1), hlit));
                 if (e & E_NONLIT) { pend = e; state = ST_PARKED; break; }
                 br.pos += e >> 8;
-                em.literal(e);
+                em.literal_deferred(e, f_lo, f_hi, full);
             }
         }
         // Lanes leave the loop at different steps: re-converge them here, or the compiler threads each break edge straight into
         // the parked code and the warp executes it once per leaving group (measured: 3 x per round at 5 of 32 lanes).
         __syncwarp();
+        if (full) em.store_deferred(f_lo, f_hi);
         // ---- parked: lengths, distances, end of block, long codes ----
         if (state == ST_PARKED) {
             const int r = parked_step(br, em, M, bc, sp, lut, state, pend);
@@ -620,12 +695,15 @@ inflate_lut_kernel(BatchArgs a) {
 int launch_lut(const BatchArgs &a, cudaStream_t stream) {
     int st = configure_once(CFG_INFLATE_K1L, [](DeviceCtx &) {
         SWC_CUDA_TRY(cudaFuncSetAttribute(k1l::inflate_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1l::SMEM_BYTES));
+        SWC_CUDA_TRY(cudaFuncSetAttribute(k1l::inflate_lut_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         return (int)SWC_OK;
     });
     if (st) return st;
+    // Persistent lanes: one CTA per resident slot.  (Launching fewer, less crowded lanes so that n / lanes lands just under a
+    // whole number of unit-times was measured slower: 74.7 ms at 14 warps per SM against 69.3 ms at 16 for 262 144 units.)
     const u64 per_cta = k1l::WARPS_PER_CTA * 32;
     u64 grid = (a.n + per_cta - 1) / per_cta;
-    const u64 resident = (u64)device_ctx().num_sms * k1l::CTAS_PER_SM;       // persistent lanes: one CTA per resident slot
+    const u64 resident = (u64)device_ctx().num_sms * k1l::CTAS_PER_SM;
     if (grid > resident) grid = resident;
     k1l::inflate_lut_kernel<<<(unsigned)grid, k1l::WARPS_PER_CTA * 32, k1l::SMEM_BYTES, stream>>>(a);
     count_launch();

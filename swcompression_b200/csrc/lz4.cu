@@ -219,6 +219,22 @@ __global__ void __launch_bounds__(128) lz4_parse_kernel(Args a, const u64 *rec_b
     rec_count[unit] = nrec;
 }
 
+// n (< 64) bytes by a 4-lane sub-group, non-overlapping: four bytes per lane and trip, the loads issued before the first store
+__device__ __forceinline__ void group_copy(u8 *dst, const u8 *src, u32 n, u32 t) {
+    for (u32 k = t; k < n; k += 16) {
+        const bool p1 = k + 4 < n, p2 = k + 8 < n, p3 = k + 12 < n;
+        const u8 b0 = src[k];
+        u8 b1 = 0, b2 = 0, b3 = 0;
+        if (p1) b1 = src[k + 4];
+        if (p2) b2 = src[k + 8];
+        if (p3) b3 = src[k + 12];
+        dst[k] = b0;
+        if (p1) dst[k + 4] = b1;
+        if (p2) dst[k + 8] = b2;
+        if (p3) dst[k + 12] = b3;
+    }
+}
+
 __global__ void __launch_bounds__(256) lz4_exec_kernel(Args a, const u64 *rec_base_idx, const u64 *recs, const u32 *rec_count) {
     const u64 unit = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (unit >= a.n) return;
@@ -257,7 +273,7 @@ __global__ void __launch_bounds__(256) lz4_exec_kernel(Args a, const u64 *rec_ba
         for (u32 b0 = 0; b0 < 32; b0 += 8) {
             const u32 l = __shfl_sync(SWC_FULL, lit, b0 + sub);
             const u32 sp = __shfl_sync(SWC_FULL, lit_src, b0 + sub), dp = __shfl_sync(SWC_FULL, lit_dst, b0 + sub);
-            if (l < 64) for (u32 i = t; i < l; i += 4) out[dp + i] = in[sp + i];
+            if (l < 64) group_copy(out + dp, in + sp, l, t);
         }
         __syncwarp();
         // ---- matches
@@ -286,9 +302,13 @@ __global__ void __launch_bounds__(256) lz4_exec_kernel(Args a, const u64 *rec_ba
                 } else {
                     const bool ready = pend && l < 64 && (sub == oldest || src_end <= (i64)fs);
                     if (ready) {
-                        for (u32 i = t; i < l; i += 4) {
-                            const i64 q = src0 + (i64)(d >= l ? i : i % d);
-                            out[s + i] = q >= 0 ? out[q] : dict_end[q];
+                        if (src0 >= 0 && d >= l) {
+                            group_copy(out + s, out + src0, l, t);
+                        } else {
+                            for (u32 i = t; i < l; i += 4) {
+                                const i64 q = src0 + (i64)(d >= l ? i : i % d);
+                                out[s + i] = q >= 0 ? out[q] : dict_end[q];
+                            }
                         }
                         pend = false;
                     }

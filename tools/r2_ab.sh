@@ -1,8 +1,8 @@
+# A/B of library variants under gpurun_ab/ (and the baseline copy at the repo root) on the headline workload
 cd /root/repo
-python -m pytest tests/test_gpu_deflate.py tests/test_gpu_differential.py -m gpu -x -q 2>&1 | tail -2
-python bench.py --steps 5 --warmup 2 --no-e2e --no-cpu > gpurun_out/ab_k2r.json 2> gpurun_out/ab_k2r.err || tail -3 gpurun_out/ab_k2r.err
-python -c "
-import json; d=json.load(open('gpurun_out/ab_k2r.json')); print('K2r', round(d['value'],1), round(d['ms_per_step'],2), d['roofline']['kernels_ms'])"
-SWC_DEFLATE_K2=old python bench.py --steps 5 --warmup 2 --no-e2e --no-cpu > gpurun_out/ab_k2o.json 2> gpurun_out/ab_k2o.err
-python -c "
-import json; d=json.load(open('gpurun_out/ab_k2o.json')); print('K2 old', round(d['value'],1), round(d['ms_per_step'],2), d['roofline']['kernels_ms'])"
+for so in ${VARIANTS:-libswcgpu_base.so gpurun_ab/*.so}; do
+  name=$(basename $so .so)
+  SWCGPU_SO=/root/repo/$so timeout 600 python bench.py --steps 3 --warmup 2 --no-e2e --no-cpu --no-legs > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err || { echo "$name FAILED"; tail -3 gpurun_out/ab_$name.err; continue; }
+  python -c "
+import json; d=json.load(open('gpurun_out/ab_$name.json')); print('$name', round(d['value'],1), 'GB/s', round(d['ms_per_step'],2), 'ms', {k: round(v,2) for k,v in d['roofline']['kernels_ms'].items()})"
+done

@@ -509,11 +509,13 @@ inflate_huffman_kernel(BatchArgs a) {
 // period: every source byte lies in [start-dist, start), never in what the match itself writes.
 __global__ void __launch_bounds__(256)
 lz_resolve_kernel(BatchArgs a) {
+    __shared__ uint4 stage[8][32];                       // {start, length, distance} of the warp's current 32 records
     const u64 unit = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (unit >= a.n) return;
     if (a.status[unit] != SWC_OK) return;
     const u32 lane = threadIdx.x & 31;
     const u32 sub = lane >> 2, t = lane & 3;
+    uint4 *st = stage[(threadIdx.x >> 5) & 7];
     const u32 nrec = a.rec_count[unit];
     const u32 *rec = a.rec_base + rec_start(a.out_off[unit]);
     u8 *out = a.out_base + a.out_off[unit];
@@ -529,21 +531,20 @@ lz_resolve_kernel(BatchArgs a) {
             const u32 v = __shfl_up_sync(SWC_FULL, end, d);
             if (lane >= (u32)d) end += v;
         }
-        const u32 start = base + end - len;
-        const u32 dist = (r & 0x7FFFu) + 1;
+        // a sub-group fetches its record with one 16-byte shared-memory load instead of three shuffles
+        st[lane] = make_uint4(base + end - len, len, (r & 0x7FFFu) + 1, 0u);
         base += __shfl_sync(SWC_FULL, end, 31);
+        __syncwarp();
 #pragma unroll 1
         for (u32 b0 = 0; b0 < 32; b0 += 8) {
-            // this sub-group's record
-            const u32 s = __shfl_sync(SWC_FULL, start, b0 + sub);
-            const u32 l = __shfl_sync(SWC_FULL, len, b0 + sub);
-            const u32 d = __shfl_sync(SWC_FULL, dist, b0 + sub);
+            const uint4 rc = st[b0 + sub];                               // this sub-group's record
+            const u32 s = rc.x, l = rc.y, d = rc.z;
             const u32 src_end = s - d + (l < d ? l : d);
             bool pend = l != 0;
             u32 pmask = __ballot_sync(SWC_FULL, pend && t == 0);         // bit 4*sub per pending record
             while (pmask) {
                 const u32 oldest = (__ffs(pmask) - 1) >> 2;                // sub-group index of the oldest pending record
-                const u32 frontier = __shfl_sync(SWC_FULL, s, oldest << 2);
+                const u32 frontier = st[b0 + oldest].x;
                 const bool ready = pend && (sub == oldest || src_end <= frontier);
                 if (ready) {
                     const u8 *src = out + s - d;
@@ -553,12 +554,12 @@ lz_resolve_kernel(BatchArgs a) {
                         // average: one trip covers 16)
                         for (u32 k = t; k < l; k += 16) {
                             const bool p1 = k + 4 < l, p2 = k + 8 < l, p3 = k + 12 < l;
-                            const u8 b0 = src[k];
+                            const u8 b0v = src[k];
                             u8 b1 = 0, b2 = 0, b3 = 0;
                             if (p1) b1 = src[k + 4];
                             if (p2) b2 = src[k + 8];
                             if (p3) b3 = src[k + 12];
-                            dst[k] = b0;
+                            dst[k] = b0v;
                             if (p1) dst[k + 4] = b1;
                             if (p2) dst[k + 8] = b2;
                             if (p3) dst[k + 12] = b3;
@@ -572,6 +573,7 @@ lz_resolve_kernel(BatchArgs a) {
                 pmask = __ballot_sync(SWC_FULL, pend && t == 0);
             }
         }
+        __syncwarp();                                                    // the stage is rewritten for the next group
     }
 }
 

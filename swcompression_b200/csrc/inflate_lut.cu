@@ -68,6 +68,14 @@ constexpr size_t SMEM_BYTES = (size_t)WARPS_PER_CTA * RING_BYTES + LUT_WORDS * 4
 constexpr int KLIT = SWC_KLIT2;             // lookups a lane may do per round (<= 56 bits) before parked symbols are serviced
 static_assert(SWC_KLIT2 <= 8, "at most one 8-byte literal word may fill up per round (deferred store)");
 
+#ifndef SWC_PATIENCE_SHIFT
+#define SWC_PATIENCE_SHIFT 3
+#endif
+#ifndef SWC_HDR_BATCH
+#define SWC_HDR_BATCH 6
+#endif
+constexpr int HDR_BATCH = SWC_HDR_BATCH;    // lanes that gather at a block boundary before the warp parses their headers
+
 constexpr u32 E_NONLIT = 0x8000u;           // LUT entry: bit15 = not a literal; [11:8] code length (0 = long / no code)
 constexpr u32 CODE_EOB = 31;                //   non-literal low byte: 0..28 length symbol 257+k, 29/30 = 286/287, 31 = end of block
 
@@ -609,43 +617,65 @@ inflate_lut_kernel(BatchArgs a) {
 #endif
     br.pos = 0; br.wend = 32; br.rptr = 0; br.wr = 0; br.nextc = 0; br.pre = make_uint4(0, 0, 0, 0);
     em.out = nullptr; em.rec = nullptr; em.op = 0; em.cap = 0; em.last_end = 0; em.nrec = 0; em.acc_lo = em.acc_hi = 0; em.dirty = false;
+    u32 rounds = 0, patience = 0;     // rounds spent on the current unit / rounds an idle lane still waits for its warp
     for (;;) {
-        if (state == ST_DONE) {
-            if (have_unit) {                                                             // retire the finished unit
-                em.finish();
-                if (status == SWC_OK && (u64)em.op > cap64) status = SWC_ERR_OUTPUT_OVERFLOW;
-                a.consumed_bits[unit] = br.pos - sp.pos0;
-                a.out_len[unit] = em.op;
-                a.status[unit] = status;
-                a.rec_count[unit] = em.nrec;
-                have_unit = false;
-            }
-            if (!exhausted) {
-                unit = atomicAdd(a.ticket + 1, 1ull);
-                if (unit >= a.n) {
-                    exhausted = true;
-                } else {
-                    have_unit = true;
-                    status = SWC_OK;
-                    const u64 in_len = a.in_len[unit];
-                    cap64 = a.out_cap[unit];
-                    em.out = a.out_base + a.out_off[unit];
-                    em.rec = a.rec_base + rec_start(a.out_off[unit]);
-                    em.cap = cap64 > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (u32)cap64;
-                    em.op = 0; em.last_end = 0; em.nrec = 0; em.acc_lo = em.acc_hi = 0; em.dirty = false;
-                    const u32 bitskip = a.start_bits ? a.start_bits[unit] : 0;
-                    sp.ubeg = a.in_base + a.in_off[unit];
-                    sp.uend = sp.ubeg + in_len;
-                    sp.origin = (const u8 *)((uintptr_t)sp.ubeg & ~(uintptr_t)15);
-                    sp.pos0 = (u32)(sp.ubeg - sp.origin) * 8 + bitskip;
-                    sp.end = sp.pos0 + (u32)(in_len * 8 - bitskip);
-                    br.pos = sp.pos0;
-                    if (in_len >= (1ull << 28)) status = SWC_ERR_UNSUPPORTED;            // bit positions are 32-bit here
-                    else if (in_len * 8 - bitskip < 10) status = SWC_DEFLATE_WRONG_BLOCK_TYPE;      // Deflate.swift:36
-                    else state = ST_HEADER;
+        if (state == ST_DONE && have_unit) {                                             // retire the finished unit
+            em.finish();
+            if (status == SWC_OK && (u64)em.op > cap64) status = SWC_ERR_OUTPUT_OVERFLOW;
+            a.consumed_bits[unit] = br.pos - sp.pos0;
+            a.out_len[unit] = em.op;
+            a.status[unit] = status;
+            a.rec_count[unit] = em.nrec;
+            have_unit = false;
+            patience = rounds >> SWC_PATIENCE_SHIFT;
+        }
+        // Unit hand-out.  A unit keeps a lane busy for thousands of rounds, so WHEN lanes start matters: lanes that run in phase
+        // share the header code (one pass serves all 32), finish together, and leave no tail of half-empty warps at the end of
+        // the batch (measured with one lane-at-a-time ticket per finished lane: the first unit of every lane took 13.2 ms, the
+        // following ones ~20 ms each).  So a warp takes 32 consecutive units at once when all its lanes are idle; an idle lane
+        // waits for that moment for at most 1/2^PATIENCE_SHIFT of the rounds its last unit took (units of similar size stay in
+        // phase) and takes a unit of its own when its patience runs out (units of very different sizes).
+        const bool idle = state == ST_DONE && !exhausted;                                // have_unit is false here
+        const u32 idle_mask = __ballot_sync(SWC_FULL, idle);
+        if (idle_mask) {
+            const u32 working = __ballot_sync(SWC_FULL, state != ST_DONE);
+            const bool take = idle && (working == 0 || patience == 0);
+            if (idle && !take) patience--;
+            const u32 take_mask = __ballot_sync(SWC_FULL, take);
+            if (take_mask) {
+                u64 first = 0;
+                const u32 leader = __ffs(take_mask) - 1;
+                if (lane == leader) first = atomicAdd(a.ticket + 1, (u64)__popc(take_mask));
+                first = __shfl_sync(SWC_FULL, first, leader);
+                if (take) {
+                    unit = first + __popc(take_mask & ((1u << lane) - 1));
+                    rounds = 0;
+                    if (unit >= a.n) {
+                        exhausted = true;
+                    } else {
+                        have_unit = true;
+                        status = SWC_OK;
+                        const u64 in_len = a.in_len[unit];
+                        cap64 = a.out_cap[unit];
+                        em.out = a.out_base + a.out_off[unit];
+                        em.rec = a.rec_base + rec_start(a.out_off[unit]);
+                        em.cap = cap64 > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (u32)cap64;
+                        em.op = 0; em.last_end = 0; em.nrec = 0; em.acc_lo = em.acc_hi = 0; em.dirty = false;
+                        const u32 bitskip = a.start_bits ? a.start_bits[unit] : 0;
+                        sp.ubeg = a.in_base + a.in_off[unit];
+                        sp.uend = sp.ubeg + in_len;
+                        sp.origin = (const u8 *)((uintptr_t)sp.ubeg & ~(uintptr_t)15);
+                        sp.pos0 = (u32)(sp.ubeg - sp.origin) * 8 + bitskip;
+                        sp.end = sp.pos0 + (u32)(in_len * 8 - bitskip);
+                        br.pos = sp.pos0;
+                        if (in_len >= (1ull << 28)) status = SWC_ERR_UNSUPPORTED;        // bit positions are 32-bit here
+                        else if (in_len * 8 - bitskip < 10) status = SWC_DEFLATE_WRONG_BLOCK_TYPE;  // Deflate.swift:36
+                        else state = ST_HEADER;
+                    }
                 }
             }
         }
+        rounds++;
         if (!__any_sync(SWC_FULL, state != ST_DONE || have_unit || !exhausted)) break;
         if (state == ST_SYMBOLS) {
             br.topup(ring, sp);
@@ -675,7 +705,12 @@ inflate_lut_kernel(BatchArgs a) {
         }
         __syncwarp();
         // ---- header: lanes at a block boundary ----
-        if (state == ST_HEADER) {
+        // A header costs the warp ~100 K instructions whether one lane parses or all 32 do, and in steady state the lanes of a
+        // warp reach their block boundaries one by one.  Lanes therefore wait at the boundary until HDR_BATCH of them have
+        // gathered (or nobody is left decoding), so that one pass over the header code serves several streams.
+        const u32 at_header = __ballot_sync(SWC_FULL, state == ST_HEADER);
+        const u32 decoding = __ballot_sync(SWC_FULL, state == ST_SYMBOLS || state == ST_PARKED);
+        if (state == ST_HEADER && (__popc(at_header) >= HDR_BATCH || decoding == 0)) {
             HeaderBits hb;
             hb.sp = sp; hb.pos = br.pos;
             int next = ST_DONE;

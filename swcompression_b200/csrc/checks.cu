@@ -145,22 +145,41 @@ int crc64(const u8 *d, u64 n, u64 *d_result, u64 *d_partial, cudaStream_t s) { r
 int adler32(const u8 *d, u64 n, u64 *d_result, u64 *d_partial, cudaStream_t s) { return run<3>(d, n, d_result, d_partial, s); }
 
 // ---------------------------------------------------------------- CRC-32 of many buffers: one warp per buffer
-// Each lane folds one of 32 contiguous segments with the byte table (shared memory), then the 32 conditioned values are
-// chained with x^(8*len) multiplications — the same identity as above, inside one warp.
+// Each lane folds one of 32 contiguous segments (a multiple of 16 bytes, read with 16-byte loads) four bytes per step with
+// four byte tables in shared memory ("slicing by 4": 2.8 instead of 6 instructions per byte), then the 32 conditioned values
+// are chained with x^(8*len) multiplications — the same identity as above, inside one warp.
+__device__ __forceinline__ u32 crc_word(const u32 (*tab)[256], u32 c, u32 w) {
+    c ^= w;
+    return tab[3][c & 0xFF] ^ tab[2][(c >> 8) & 0xFF] ^ tab[1][(c >> 16) & 0xFF] ^ tab[0][c >> 24];
+}
 __global__ void __launch_bounds__(256) crc32_units_kernel(const u8 *base, const u64 *off, const u64 *len, const int32_t *status, u32 *result, u64 n) {
-    __shared__ u32 tab[256];
-    for (u32 i = threadIdx.x; i < 256; i += blockDim.x) { u32 c = i; for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1; tab[i] = c; }
+    __shared__ u32 tab[4][256];
+    for (u32 i = threadIdx.x; i < 256; i += blockDim.x) {
+        u32 c = i;
+        for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+        tab[0][i] = c;
+    }
     __syncthreads();
+    for (int t = 1; t < 4; t++) {
+        for (u32 i = threadIdx.x; i < 256; i += blockDim.x) { const u32 c = tab[t - 1][i]; tab[t][i] = (c >> 8) ^ tab[0][c & 0xFF]; }
+        __syncthreads();
+    }
     const u64 unit = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (unit >= n) return;
     const u32 lane = threadIdx.x & 31;
     const u8 *p = base + off[unit];
     // a unit that did not decode cleanly has no defined extent (Deflate reports the size it WOULD need on overflow): skip it
     const u64 L = (status && status[unit] != SWC_OK) ? 0 : len[unit];
-    const u64 seg = (L + 31) / 32;
+    const u64 seg = (((L + 31) / 32) + 15) & ~(u64)15;
     const u64 sb = lane * seg < L ? lane * seg : L, se = sb + seg < L ? sb + seg : L;
     u32 c = 0xFFFFFFFFu;
-    for (u64 i = sb; i < se; i++) c = tab[(c ^ p[i]) & 0xFF] ^ (c >> 8);
+    u64 i = sb;
+    for (; i < se && ((uintptr_t)(p + i) & 15); i++) c = tab[0][(c ^ p[i]) & 0xFF] ^ (c >> 8);
+    for (; i + 16 <= se; i += 16) {
+        const uint4 v = __ldg((const uint4 *)(p + i));
+        c = crc_word(tab, c, v.x); c = crc_word(tab, c, v.y); c = crc_word(tab, c, v.z); c = crc_word(tab, c, v.w);
+    }
+    for (; i < se; i++) c = tab[0][(c ^ p[i]) & 0xFF] ^ (c >> 8);
     c = ~c;
     const u32 pw = xpow32r(seg);
     u32 acc = __shfl_sync(0xFFFFFFFFu, c, 0);

@@ -8,8 +8,8 @@
 //        decode tables live in shared memory, word-interleaved across the 32 lanes so that lane l only ever touches
 //        bank l (conflict-free for any index pattern).  The compressed stream is fetched with 16-byte streaming loads,
 //        double-buffered in registers one chunk ahead of the bit buffer.
-//   K2 lz_resolve_kernel       — ONE WARP PER UNIT. Replays the records in order; each match is copied by the 32 lanes
-//        (period-replicating when distance < length).  Positions come from a warp inclusive scan of the records.
+//   K2 lz_resolve_kernel       — ONE WARP PER UNIT. Replays the records 8 at a time on 4-lane sub-groups (period-replicating
+//        when distance < length).  Positions come from a warp inclusive scan of the records.
 //
 // Semantics are those of the reference, including its error cases and the inputs on which it traps
 // (SWC_ERR_REFERENCE_TRAP).  Code sets whose Kraft sum exceeds 1 (which the reference accepts through heap-slot
@@ -501,8 +501,8 @@ inflate_huffman_kernel(BatchArgs a) {
 
 // ------------------------------------------------------------------------------------------------ K2
 // One warp per unit: replay the match records in order.  Lane j holds record j of a 32-record group; an inclusive warp
-// scan of (literal-run + length) gives every match its absolute position.  The group is then executed 8 records at a
-// time by 4-lane sub-groups.  A record is READY when everything it reads is final: its source ends at or before the
+// scan of (literal-run + length) gives every match its absolute position; {start, length, distance} are staged in shared
+// memory.  The group is then executed 8 records at a time by 4-lane sub-groups (one 16-byte load fetches the record).  A record is READY when everything it reads is final: its source ends at or before the
 // start of the oldest still-pending record of the batch (bytes before that point were placed by K1 literals or by
 // completed matches) — or it IS that oldest record.  Far matches therefore run 8-wide in one pass; chains of
 // near matches (RLE-like data) degrade gracefully to in-order execution.  Overlapping copies (dist < len) replicate the

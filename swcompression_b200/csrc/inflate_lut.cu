@@ -4,19 +4,22 @@
 // Same contract as inflate_huffman_kernel (inflate.cu): literals land at their final output position, every match
 // becomes a 4-byte record {dist-1:15 | esc:1 | len-3:8 | literal-run:8} for lz_resolve_kernel.
 //
-// 32 different streams per warp, persistent lanes fed by a ticket counter.  A warp works in rounds that start with a
-// full-mask vote (lanes stay in lock step):
+// 32 different streams per warp, persistent lanes.  Units are handed out 32 at a time to a warp whose lanes are all idle, so the
+// lanes of a warp run in phase (see the hand-out comment in the kernel).  A warp works in rounds that start with a full-mask vote:
 //   top-up : every lane keeps an 8-word ring of its compressed stream in shared memory; a lane whose ring is half empty
 //            stores the 16-byte chunk it prefetched a round earlier (one LDG.128 per lane) and issues the next
 //            load — the only place global input is touched, so the load latency never sits on the decode chain.
-//   fast   : up to KLIT table lookups per lane: peek (funnel shift of a 64-bit register window) -> 2^8-entry 16-bit LUT in
-//            shared memory, halfword-interleaved across the warp (entry h of lane l at halfword h*32+l: at most a 2-way bank
-//            conflict) -> literal: merged into the 8-byte word that is stored at its final position; anything else
-//            (length, end of block, code longer than 8 bits) parks the lane, which leaves the loop.
-//   parked : all parked lanes together: length extra bits, distance code (2^5-entry LUT, canonical limit-compare decoder for
-//            longer codes), reference checks (Deflate.swift:199-232), one record per match.
-//   header : block headers (Deflate.swift:41-168) are parsed by the lanes that reached one, with a plain global-memory bit
-//            reader; short codes fill the LUTs, long ones go to sorted lists for the canonical decoder.
+//   fast   : up to KLIT table lookups per lane: peek (funnel shift of a 64-bit register window, refilled without a branch, the
+//            next ring word already in a register) -> 2^7-entry 16-bit LUT in shared memory, halfword-interleaved across the
+//            warp (entry h of lane l at halfword h*32+l: conflict-free) -> literal: shifted into the 8-byte word of its final
+//            position (the word that fills up is stored once, after the loop); anything else (length, end of block, code
+//            longer than 7 bits) parks the lane, which leaves the loop.
+//   parked : all parked lanes together: length extra bits, distance code (2^5-entry 8-bit LUT, canonical limit-compare decoder
+//            for longer codes), reference checks (Deflate.swift:199-232), one record per match.
+//   header : block headers (Deflate.swift:41-168) are parsed by the lanes that reached one (they wait for HDR_BATCH of them),
+//            with a plain global-memory bit reader; short codes fill the LUTs, long ones go to sorted lists for the
+//            canonical decoder.  Per-length counters / cursors live in local memory; shared memory keeps 12.3 KB per warp
+//            (LUTs, 18 long-code base words, ring): 16 resident warps per SM.
 // Input availability (the reference's bitsLeft guards) is checked lazily against an absolute bit position: reads past the
 // unit return zero bits and the first field that crosses the end reports symbolNotFound exactly as the reference does.
 // Code sets with Kraft sum > 1 go to inflate_slow_kernel via SWC_INTERNAL_NEEDS_SLOW (same contract as K1).

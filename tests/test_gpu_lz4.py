@@ -56,6 +56,36 @@ def test_block_batch_config3_shape(oracle):
         assert st[i] == ost == 0 and outs[i] == oout == raws[i], i
 
 
+def test_benched_config_two_phase_kernels_all_units(oracle):
+    """BASELINE configs[2] shape through the kernels tools/bench_codecs.py times: 20 480 independent 64 KiB blocks (256 distinct:
+    80 % text-like, 10 % zeros, 10 % incompressible) take lz4_parse_kernel + lz4_exec_kernel in one call.  Every distinct block is
+    compared byte for byte with the oracle, and every tiled copy with the first copy on the device."""
+    import numpy as np
+    import torch  # noqa: F401
+    from swcompression_b200.batch import Batch, pack_units
+    rng = random.Random(33)
+    raws = []
+    for i in range(256):
+        k = rng.random()
+        raws.append(bytes(65536) if k < 0.1 else bytes(rng.getrandbits(8) for _ in range(65536)) if k < 0.2 else H.textlike(65536, 700 + i))
+    units = [H.lz4_block_compress(r) for r in raws]
+    buf, offs, lens = pack_units(units)
+    stride, tile = len(buf) - 64, 80
+    big = np.concatenate([np.tile(buf[:stride], tile), np.zeros(64, dtype=np.uint8)])
+    all_off = (offs[None, :] + (np.arange(tile, dtype=np.uint64) * np.uint64(stride))[:, None]).reshape(-1)
+    b = Batch("lz4_block", big, all_off, np.tile(lens, tile), 65536)
+    assert b.n == 20480
+    b.run()
+    st, ln, _ = b.results()
+    assert (st == 0).all() and (ln == 65536).all()
+    out = b.d_out[: b.n * 65536].view(tile, 256, 65536)
+    assert bool((out == out[0:1]).all()), "tiled copies differ"
+    first = out[0].cpu().numpy()
+    for i, u in enumerate(units):
+        ost, oout, _ = oracle.lz4_block(u)
+        assert ost == 0 and bytes(first[i]) == oout == raws[i], i
+
+
 def test_block_ragged_and_fuzz(oracle):
     rng = random.Random(4)
     units = []

@@ -145,16 +145,11 @@ __device__ __forceinline__ u32 lut_addr(u32 index, u32 base) { u32 a; asm("mad.l
 // ------------------------------------------------------------------------------------------------ symbol-phase bit reader
 // Window (lo, hi) = stream words [wend/32 - 1, wend/32]; further words wait in the shared-memory ring (slot = word index & 7,
 // slot k of lane l at ring + k*128 + l*4; the ring of a warp is 1 KiB-aligned so the slot address wraps with one LOP3).
-#ifndef SWC_NXT
-#define SWC_NXT 1
-#endif
 struct Reader {
     u32 lo, hi;
-#if SWC_NXT
     u32 nxt;          // stream word wend/32 + 1, popped one step early so that no shared-memory load sits on the decode chain
-#endif
     u32 pos;          // absolute bit position of the next unread bit;  wend - 32 <= pos < wend + 32
-    u32 wend;         // bit position where `hi` starts; the next word to pop has index wend/32 + 1 (+ 2 with `nxt`)
+    u32 wend;         // bit position where `hi` starts; the next word to pop from the ring has index wend/32 + 2
     u32 rptr;         // shared-memory address of that word's slot
     u32 wr;           // next word index to push into the ring
     u32 nextc;        // chunk index after `pre`
@@ -163,12 +158,8 @@ struct Reader {
     __device__ __forceinline__ u32 peek32() const { return __funnelshift_r(lo, hi, pos); }   // requires pos < wend
     __device__ __forceinline__ void advance() {                                                // requires pos >= wend
         lo = hi;
-#if SWC_NXT
         hi = nxt;
         nxt = lds32(rptr);
-#else
-        hi = lds32(rptr);
-#endif
         const u32 t = rptr + 128;
         rptr = (t & 0x380u) | (rptr & ~0x380u);
         wend += 32;
@@ -179,17 +170,13 @@ struct Reader {
         const u32 nw = lds32(rptr);
         const u32 t = rptr + 128;
         lo = adv ? hi : lo;
-#if SWC_NXT
         hi = adv ? nxt : hi;
         nxt = adv ? nw : nxt;
-#else
-        hi = adv ? nw : hi;
-#endif
         rptr = adv ? ((t & 0x380u) | (rptr & ~0x380u)) : rptr;
         wend = adv ? wend + 32 : wend;
     }
     __device__ __forceinline__ void topup(u32 *ring, const Span &sp) {
-        if (wr - (wend >> 5) <= 5 + SWC_NXT) {                     // <= 4 unread words in the ring: chunk wr/4 - 2 is consumed
+        if (wr - (wend >> 5) <= 6) {                                   // <= 4 unread words in the ring: chunk wr/4 - 2 is consumed
             u32 *s = ring + (wr & 4) * 32;
             s[0] = pre.x; s[32] = pre.y; s[64] = pre.z; s[96] = pre.w;
             wr += 4;
@@ -208,10 +195,8 @@ struct Reader {
         wr = (ch + 2) * 4;
         lo = ring[(w0 & 7) * 32];
         hi = ring[((w0 + 1) & 7) * 32];
-#if SWC_NXT
         nxt = ring[((w0 + 2) & 7) * 32];
-#endif
-        rptr = (u32)__cvta_generic_to_shared(ring + ((w0 + 2 + SWC_NXT) & 7) * 32);
+        rptr = (u32)__cvta_generic_to_shared(ring + ((w0 + 3) & 7) * 32);
         wend = (w0 + 1) * 32;
         pos = bit;
     }
@@ -614,10 +599,7 @@ inflate_lut_kernel(BatchArgs a) {
     u64 cap64 = 0;
     u32 pend = 0;
     sp.origin = sp.ubeg = sp.uend = nullptr; sp.pos0 = sp.end = 0;
-    br.lo = br.hi = 0;
-#if SWC_NXT
-    br.nxt = 0;
-#endif
+    br.lo = br.hi = br.nxt = 0;
     br.pos = 0; br.wend = 32; br.rptr = 0; br.wr = 0; br.nextc = 0; br.pre = make_uint4(0, 0, 0, 0);
     em.out = nullptr; em.rec = nullptr; em.op = 0; em.cap = 0; em.last_end = 0; em.nrec = 0; em.acc_lo = em.acc_hi = 0; em.dirty = false;
     u32 rounds = 0, patience = 0;     // rounds spent on the current unit / rounds an idle lane still waits for its warp
